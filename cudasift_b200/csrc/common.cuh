@@ -1,0 +1,112 @@
+// common.cuh -- internal declarations shared by the cudasift_b200 translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstdint>
+
+#include "../../include/cudaSift.h"
+#include "../../include/cudasift_b200.h"
+
+#define CS_NUM_SCALES 5                    // cudaSiftD.h:8
+#define CS_LAPLACE_S (CS_NUM_SCALES + 3)   // 8 blurred scales -> 7 DoG planes
+#define CS_MAX_LEVELS 8                    // d_PointCounter[8*2+1], cudaSiftD.cu:14
+
+static_assert(sizeof(SiftPoint) == 576, "SiftPoint layout is ABI");
+static_assert(sizeof(SiftData) == 24, "SiftData layout is ABI");
+static_assert(sizeof(CudaImage) == 48, "CudaImage layout is ABI");
+
+namespace cs {
+
+// ---- error handling -------------------------------------------------------------
+// The C ABI reports errors through return codes + cs_last_error(); the drop-in C++ API
+// keeps the reference's "message on stderr, exit(-1)" contract (cudautils.h:15-39).
+void set_error(const char *fmt, ...);
+extern thread_local bool g_exit_on_error;
+
+#define CS_CUDA(call)                                                                   \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess) {                                                            \
+      ::cs::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                      cudaGetErrorString(e_));                                          \
+      if (::cs::g_exit_on_error) {                                                      \
+        fprintf(stderr, "cudasift_b200: %s\n", cs_last_error());                        \
+        exit(-1);                                                                       \
+      }                                                                                 \
+      return CS_E_CUDA;                                                                 \
+    }                                                                                   \
+  } while (0)
+
+extern unsigned long long g_launches;   // kernels launched by this library
+inline void count_launch(int n = 1) { g_launches += n; }
+
+// ---- filter taps (host) ----------------------------------------------------------
+void scaledown_taps(float variance, float k[5]);                  // cudaSiftH.cu:315-324
+void lowpass_taps(float sigma, float k[9]);                       // cudaSiftH.cu:408-419
+void laplace_taps(int numOctaves, float initBlur, float *kernel); // cudaSiftH.cu:439-458
+
+struct Taps9 { float k[9]; };
+struct Taps5 { float k[5]; };
+struct LaplaceTaps { float k[CS_LAPLACE_S][5]; };   // [scale][tap], tap 0 = centre
+
+// ---- pyramid ----------------------------------------------------------------------
+int launch_lowpass(const float *src, int srcPitch, float *dst, int dstPitch, int w, int h,
+                   const Taps9 &taps, cudaStream_t st);
+int launch_scaledown(const float *src, float *dst, int w, int h, int pitch, int newpitch,
+                     const Taps5 &taps, cudaStream_t st);
+int launch_scaleup(const float *src, float *dst, int w, int h, int pitch, int newpitch,
+                   cudaStream_t st);
+
+// ---- detection ---------------------------------------------------------------------
+struct DetectLevel {
+  const float *img;     // octave base image
+  int w, h, pitch;
+  int tilesX, tilesY;
+  int tileBase;         // first linear block id of this level
+  float subsampling;
+  float lowestScale;    // lowestScale / subsampling, cudaSiftH.cu:213
+  LaplaceTaps taps;
+};
+struct DetectParams {
+  DetectLevel lev[CS_MAX_LEVELS];
+  int numLevels;
+  int totalTiles;
+  float thresh, edgeLimit, factor;
+  SiftPoint *pts;
+  unsigned int *counters;   // [0] detected (primaries), [1] total incl. secondaries
+  int maxPts;
+};
+int launch_detect(const DetectParams &p, cudaStream_t st);
+int launch_dog_planes(const float *base, float *dog, int w, int h, int pitch,
+                      const LaplaceTaps &taps, cudaStream_t st);
+
+// ---- orientation + descriptor ---------------------------------------------------------
+struct DescribeParams {
+  cudaTextureObject_t tex[CS_MAX_LEVELS];   // indexed by log2(subsampling)
+  int numLevels;
+  SiftPoint *pts;
+  unsigned int *counters;
+  int maxPts;
+  float finestSubsampling;  // secondaries of this level are dropped (reference quirk Q1)
+};
+int launch_describe(const DescribeParams &p, int gridBlocks, cudaStream_t st);
+int launch_rescale(SiftPoint *pts, const unsigned int *counters, int maxPts, float f,
+                   cudaStream_t st);
+int launch_tex_probe(cudaTextureObject_t tex, const float *xs, const float *ys, int n,
+                     float *out, cudaStream_t st);
+
+int make_texture(cudaTextureObject_t *tex, const float *img, int w, int h, int pitch);
+
+// ---- matcher ------------------------------------------------------------------------
+struct MatchWorkspace;   // opaque, owned by the per-device context
+int match_exact(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_t st);
+int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_t st,
+                 unsigned long long stats[4]);
+bool match_tensor_supported();
+
+inline int idivup(int a, int b) { return (a + b - 1) / b; }
+inline int ialignup(int a, int b) { return (a % b != 0) ? (a - a % b + b) : a; }
+
+}  // namespace cs

@@ -1,0 +1,77 @@
+"""GPU parity of MatchSiftData: match indices (and here all five output fields) bit-exact
+against the oracle and against the reference library on identical SiftData arrays."""
+import numpy as np
+import pytest
+
+import oracle
+from cudasift_b200.synth import synth_descriptors
+
+pytestmark = pytest.mark.gpu
+FIELDS = ("score", "ambiguity", "match", "match_xpos", "match_ypos")
+
+
+def _eq(a, b, what):
+    for f in FIELDS:
+        assert np.array_equal(a[f], b[f]), "%s: field %s differs in %d rows" % (what, f, int((a[f] != b[f]).sum()))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n1,n2", [(1, 32), (100, 64), (257, 500), (1000, 1031), (2000, 2000)])
+def test_match_bit_exact_vs_oracle(cs, n1, n2, mode):
+    s1, s2 = synth_descriptors(n1, 1), synth_descriptors(n2, 2)
+    got, _ = cs.match_host(s1, s2, mode=mode)
+    _eq(got, oracle.match(s1, s2, threads=8), "mode %d %dx%d" % (mode, n1, n2))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_match_quirks(cs, mode):
+    s2, s1 = synth_descriptors(640, 5), synth_descriptors(300, 6)
+    s1["data"][0] = s2["data"][40]; s2["data"][7] = s2["data"][40]; s2["data"][33] = s2["data"][40]   # Q10 ties
+    s1["data"][1] = s2["data"][639]                       # best candidate in the unvisited tail? (640 % 32 == 0: visited)
+    s1["data"][2] *= -1                                   # Q11: no positive score
+    s1["data"][3] = 0
+    got, _ = cs.match_host(s1, s2, mode=mode)
+    want = oracle.match(s1, s2)
+    _eq(got, want, "quirks")
+    assert got["match"][0] == 33 and got["match"][2] == -1 and got["match"][3] == -1
+    got2, _ = cs.match_host(s1, s2[:630], mode=mode)      # Q7: tail of 22 ignored
+    _eq(got2, oracle.match(s1, s2[:630]), "tail")
+    got3, _ = cs.match_host(s1, s2[:31], mode=mode)       # nothing visited
+    assert np.all(got3["match"] == -1) and np.all(got3["score"] == 0)
+    # SIFT-like (clamped) descriptors and near-duplicate candidates
+    a, b = synth_descriptors(500, 11, sift_like=True), synth_descriptors(800, 12, sift_like=True)
+    b["data"][100:200] = b["data"][0:100] * np.float32(1.0) + np.float32(1e-7)
+    got4, _ = cs.match_host(a, b, mode=mode)
+    _eq(got4, oracle.match(a, b, threads=8), "near duplicates")
+
+
+@pytest.mark.parametrize("n", [2000, 10000])
+def test_match_bit_exact_vs_reference(cs, reflib, n):
+    """BASELINE.json config #3: 2000x2000 then 10000x10000 synthetic descriptors."""
+    if reflib is None:
+        pytest.skip("oracle/_ref/libcudasift_ref.so not present")
+    s1, s2 = synth_descriptors(n, 1), synth_descriptors(n, 2)
+    ref, _ = reflib.match(s1, s2)
+    for mode in (1, 2):
+        got, _ = cs.match_host(s1, s2, mode=mode)
+        _eq(got, ref, "mode %d vs reference %d" % (mode, n))
+    if n == 2000:
+        _eq(oracle.match(s1, s2, threads=8), ref, "oracle vs reference")
+
+
+def test_match_device_api(cs):
+    """MatchSiftData through the SiftData mirror (host copy of the 5 fields, matching.cu:1195-1199)."""
+    s1, s2 = synth_descriptors(300, 3), synth_descriptors(352, 4)
+    d1 = cs.InitSiftData(cs.SiftData(), 512, True, True)
+    d2 = cs.InitSiftData(cs.SiftData(), 512, False, True)
+    d1._buf.upload(s1); d2._buf.upload(s2)
+    d1.numPts, d2.numPts = 300, 352
+    ms = cs.MatchSiftData(d1, d2)
+    assert ms > 0
+    want = oracle.match(s1, s2)
+    _eq(d1.h_data[:300], want, "host copy")
+    dev = d1._buf.download(cs.SIFT_DTYPE, 300)
+    _eq(dev, want, "device records")
+    assert np.array_equal(dev["data"], s1["data"])        # descriptors untouched
+    d1.numPts = 0
+    assert cs.MatchSiftData(d1, d2) == 0.0                # matching.cu:1095-1096
