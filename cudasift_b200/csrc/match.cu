@@ -32,19 +32,25 @@ __device__ __forceinline__ void part_update(PartState &s, float sc, int p2)
   else if (sc > s.sec) s.sec = sc;
 }
 
+// rows == nullptr: the CTA handles rows [32*blockIdx.x, +32) of set 1.  rows != nullptr: it
+// handles entries [32*b, +32) of the row list (*nrows entries), b grid-strided -- the
+// fallback of the tensor-core path for rows it could not certify.
 __global__ void __launch_bounds__(MX_THREADS)
-match_exact_kernel(SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ sift2, int n1, int n2)
+match_exact_kernel(SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ sift2, int n1, int n2,
+                   const int *__restrict__ rows, const unsigned int *__restrict__ nrows)
 {
   __shared__ float4 s_a[MX_ROWS * MX_LD];
   __shared__ float4 s_b[MX_COLS * MX_LD];
   const int tid = threadIdx.x;
   const int rq = tid & 15;       // rows rq and rq+16 of the CTA's 32
   const int part = tid >> 4;     // partition 0..7 -> candidates 4*part..4*part+3 of each block
-  const int bp1 = blockIdx.x * MX_ROWS;
-
+  if (rows) n1 = (int)*nrows;
+ for (int bp1 = blockIdx.x * MX_ROWS; bp1 < n1; bp1 += gridDim.x * MX_ROWS) {
+  __syncthreads();
   for (int i = tid; i < MX_ROWS * 32; i += MX_THREADS) {
     int r = i >> 5, d = i & 31;
     int p1 = min(bp1 + r, n1 - 1);
+    if (rows) p1 = rows[p1];
     s_a[r * MX_LD + d] = reinterpret_cast<const float4 *>(sift1[p1].data)[d];
   }
   PartState st[2];
@@ -110,19 +116,29 @@ match_exact_kernel(SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ 
         else if (my > sec) sec = my;
       }
     }
-    SiftPoint *o = sift1 + bp1 + tid;
+    SiftPoint *o = sift1 + (rows ? rows[bp1 + tid] : bp1 + tid);
     o->score = mx;
     o->match = idx;
     o->match_xpos = idx >= 0 ? sift2[idx].xpos : 0.0f;
     o->match_ypos = idx >= 0 ? sift2[idx].ypos : 0.0f;
     o->ambiguity = __fdiv_rn(sec, __fadd_rn(mx, 1e-6f));
   }
+ }
 }
 
 int match_exact(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_t st)
 {
   if (n1 <= 0) return 0;
-  match_exact_kernel<<<idivup(n1, MX_ROWS), MX_THREADS, 0, st>>>(s1, s2, n1, n2);
+  match_exact_kernel<<<idivup(n1, MX_ROWS), MX_THREADS, 0, st>>>(s1, s2, n1, n2, nullptr, nullptr);
+  count_launch();
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int match_exact_rows(SiftPoint *s1, const SiftPoint *s2, int n2, const int *rows, const unsigned int *nrows,
+                     cudaStream_t st)
+{
+  match_exact_kernel<<<128, MX_THREADS, 0, st>>>(s1, s2, 0, n2, rows, nrows);
   count_launch();
   CS_CUDA(cudaGetLastError());
   return 0;
