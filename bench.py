@@ -315,7 +315,7 @@ def cpu_baseline(imgs):
     import oracle
     cores = os.cpu_count() or 1
     threads = min(cores, 32)
-    per_thread = 2
+    per_thread = 8
     oracle.extract(imgs[0], OCTAVES, INIT_BLUR, THRESH)          # warm (loads the .so)
 
     def work(i):
@@ -385,6 +385,15 @@ def run_reference(args):
         barrier_and_sync(dist)
         dte = time.perf_counter() - t0
     dt, dte = reduce_max(dist, dt), reduce_max(dist, dte)
+    match = None
+    if rank == 0:
+        from cudasift_b200.synth import synth_descriptors
+        n = 10000
+        s1, s2 = synth_descriptors(n, 1), synth_descriptors(n, 2)
+        ts = [ref.match(s1, s2)[1] for _ in range(6)][1:]
+        ms = float(np.median(ts))
+        match = {"n": n, "ms": round(ms, 4), "gpair_per_s": round(n * n / (ms * 1e-3) / 1e9, 2),
+                 "how": "reference MatchSiftData (FindMaxCorr10), its own TimerGPU incl. the 5-field D2H copy"}
     value = args.steps * B * world / dt
     e2e = esteps * B * world / dte
     if rank == 0:
@@ -403,6 +412,7 @@ def run_reference(args):
             "e2e": {"value": round(e2e, 1), "unit": "images/s", "h2d_bytes_per_step": B * W * H * 4,
                     "d2h_bytes_per_step": B * npts * 576,
                     "api": "CudaImage::Download + ExtractSift (host copy of the points included, cudaSiftH.cu:139-140)"},
+            "match": match,
         }), flush=True)
     if dist is not None:
         dist.barrier()
@@ -412,7 +422,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per step per GPU")

@@ -149,6 +149,7 @@ describe_kernel(const __grid_constant__ DescribeParams P)
       float sina = __sinf(theta), cosa = __cosf(theta);
       float scale = __fmul_rn(12.0f / 16.0f, pscale);
       float ssina = __fmul_rn(scale, sina), scosa = __fmul_rn(scale, cosa);
+      int has8 = 0;
 #pragma unroll
       for (int rep = 0; rep < 2; rep++) {
         const int sidx = tx + rep * DS_THREADS;     // sample index = y*16 + x
@@ -170,16 +171,17 @@ describe_kernel(const __grid_constant__ DescribeParams P)
         float verf = __fsub_rn(__fmul_rn(y - 1.5f, 0.25f), (float)veri), iverf = __fsub_rn(1.0f, verf);
         int angi = __float2int_rz(angf);
         angf = __fsub_rn(angf, (float)angi);
-        // Q22: angf can reach 8.0001 (angle == pi): the reference then votes out of range;
-        // here the bin wraps (8 -> 0), which is what the angle means.
-        if (angi >= 8) angi -= 8;
+        // Quirk Q22: for dy == +0, dx < 0 (edges of saturated areas) angf = 8.0001 and angi = 8;
+        // the reference then adds its "iangf" vote at flat index 8*cell + 8, i.e. into angle
+        // bin 0 of the NEXT cell (cudaSiftD.cu:353-384).  Reproduced below (has8 path).
+        has8 |= (angi >= 8);
         float gl = __fmul_rn(ihorf, grad), gr = __fmul_rn(horf, grad);
         float4 g2 = make_float4(__fmul_rn(iverf, gl), __fmul_rn(verf, gl), __fmul_rn(iverf, gr), __fmul_rn(verf, gr));
         *reinterpret_cast<float4 *>(s_g2[sidx]) = g2;
         s_angf[sidx] = angf;
         s_angi[sidx] = angi;
       }
-      __syncthreads();
+      has8 = __syncthreads_or(has8);
       {  // owner-computes gather: thread = output bin (ycell, xcell, angle)
         const int cy = tx >> 5, cx = (tx >> 3) & 3, a = tx & 7;
         const int ylo = max(0, 4 * cy - 2), yhi = min(15, 4 * cy + 5);
@@ -197,6 +199,21 @@ describe_kernel(const __grid_constant__ DescribeParams P)
               float af = s_angf[sidx];
               float wgt = (angi == a ? __fsub_rn(1.0f, af) : af);
               acc = __fadd_rn(acc, __fmul_rn(wgt, g2));
+            }
+          }
+        }
+        if (has8 && a == 0 && tx >= 8) {
+          // Q22 votes of the previous cell (flat order) land in this cell's bin 0
+          const int pc = (tx >> 3) - 1, pcy = pc >> 2, pcx = pc & 3;
+          const int y0 = max(0, 4 * pcy - 2), y1 = min(15, 4 * pcy + 5);
+          const int x0 = max(0, 4 * pcx - 2), x1 = min(15, 4 * pcx + 5);
+          for (int y = y0; y <= y1; y++) {
+            const int lower = (((y + 2) >> 2) - 1 != pcy);
+            for (int x = x0; x <= x1; x++) {
+              const int right = (((x + 2) >> 2) - 1 != pcx);
+              const int sidx = y * 16 + x;
+              if (s_angi[sidx] >= 8)
+                acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(1.0f, s_angf[sidx]), s_g2[sidx][2 * right + lower]));
             }
           }
         }

@@ -307,18 +307,24 @@ int oracle_find_points(const float *dog, int w, int h, int pitch, float subsampl
 /* ------------------------------------------------------------------ texture */
 
 float oracle_tex2d(const float *img, int w, int h, int pitch, float x, float y)
-{ /* CUDA linear filtering: xB = x-0.5, i = floor(xB), alpha = frac(xB) in 1.8 fixed point;
-     clamp addressing.  Weight quantisation: round-to-nearest on 8 fractional bits. */
-  float xb = x - 0.5f, yb = y - 0.5f;
-  float fx = floorf(xb * 256.0f + 0.5f), fy = floorf(yb * 256.0f + 0.5f);
-  float ix = floorf(fx * (1.0f / 256.0f)), iy = floorf(fy * (1.0f / 256.0f));
-  float a = (fx - ix * 256.0f) * (1.0f / 256.0f), b = (fy - iy * 256.0f) * (1.0f / 256.0f);
-  int i0 = (int)fmaxf(fminf(ix, (float)(w + 8)), -8.0f), j0 = (int)fmaxf(fminf(iy, (float)(h + 8)), -8.0f);
+{ /* CUDA linear filtering with clamp addressing and unnormalised coordinates, as measured
+     on the B200 texture unit (scripts/tex_calib.py, tests/test_tex_gpu.py):
+       fixed-point coordinate  F = floor((x - 0.5)*256 + 0.5), texel i = F >> 8, A = F & 255
+       (1.8 fixed-point weight, round to nearest); likewise B for y;
+       2-D weights in 1/256 units:  w11 = (A*B + 128) >> 8, w10 = A - w11, w01 = B - w11,
+       w00 = 256 - A - B + w11;  the weighted sum is formed exactly and rounded once. */
+  double fx = floor(((double)x - 0.5) * 256.0 + 0.5), fy = floor(((double)y - 0.5) * 256.0 + 0.5);
+  if (!(fx > -1.0e9 && fx < 1.0e9)) fx = 0.0;     /* NaN / huge coordinates */
+  if (!(fy > -1.0e9 && fy < 1.0e9)) fy = 0.0;
+  double ixd = floor(fx / 256.0), iyd = floor(fy / 256.0);
+  int A = (int)(fx - ixd * 256.0), B = (int)(fy - iyd * 256.0);
+  int i0 = (int)ixd, j0 = (int)iyd;
   int i1 = clampi(i0 + 1, 0, w - 1), j1 = clampi(j0 + 1, 0, h - 1);
   i0 = clampi(i0, 0, w - 1); j0 = clampi(j0, 0, h - 1);
-  float t00 = img[(size_t)j0 * pitch + i0], t10 = img[(size_t)j0 * pitch + i1];
-  float t01 = img[(size_t)j1 * pitch + i0], t11 = img[(size_t)j1 * pitch + i1];
-  return (1.0f - a) * (1.0f - b) * t00 + a * (1.0f - b) * t10 + (1.0f - a) * b * t01 + a * b * t11;
+  int w11 = (A * B + 128) >> 8, w10 = A - w11, w01 = B - w11, w00 = 256 - A - B + w11;
+  double t00 = img[(size_t)j0 * pitch + i0], t10 = img[(size_t)j0 * pitch + i1];
+  double t01 = img[(size_t)j1 * pitch + i0], t11 = img[(size_t)j1 * pitch + i1];
+  return (float)((w00 * t00 + w10 * t10 + w01 * t01 + w11 * t11) * (1.0 / 256.0));
 }
 
 /* ------------------------------------------------------------------ orientation */

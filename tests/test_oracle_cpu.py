@@ -91,6 +91,10 @@ def test_tex2d_matches_bilinear_with_8bit_weights():
     ref = (1 - a) * (1 - b) * img[j0, i0] + a * (1 - b) * img[j0, i1] + (1 - a) * b * img[j1, i0] + a * b * img[j1, i1]
     grad = np.abs(img[j0, i1] - img[j0, i0]) + np.abs(img[j1, i0] - img[j0, i0]) + np.abs(img[j1, i1] - img[j0, i0])
     assert np.all(np.abs(got - ref) <= grad / 256.0 + 1e-3)    # within the 1.8 fixed-point quantisation
+    # measured B200 behaviour (scripts/tex_calib.py): weights are whole 1/256ths that sum to 1
+    hot = np.zeros((16, 16), np.float32); hot[8, 8] = 65536.0
+    wq = oracle.tex2d(hot, np.array([8.59521484375, 7.955078125], np.float32), np.array([8.8134765625, 8.00048828125], np.float32))
+    assert list(wq) == [40960.0, 15104.0]
     # exact at texel centres
     assert np.allclose(oracle.tex2d(img, np.array([10.5], np.float32), np.array([7.5], np.float32)), img[7, 10])
 

@@ -27,6 +27,6 @@ def test_texture_emulation(cs):
     sw = oracle.tex2d(arr, xs, ys)
     assert np.array_equal(hw[:100], arr[10, :100])
     err = np.abs(hw - sw)
-    # identical weight quantisation -> only float rounding of the blend differs
-    assert np.quantile(err, 0.999) < 1e-3, "texture emulation off: q999=%g max=%g" % (np.quantile(err, 0.999), err.max())
-    assert err.max() < 0.25
+    # same 1.8 fixed-point weights and weight products -> only the final rounding can differ
+    assert (hw == sw).mean() > 0.99, "texture emulation: only %.4f of the fetches are bit-identical" % (hw == sw).mean()
+    assert err.max() < 1e-4, "texture emulation off: max=%g" % err.max()
