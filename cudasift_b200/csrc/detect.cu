@@ -22,7 +22,7 @@ namespace cs {
 #define DT_H 16               // DoG tile height  (14 interior rows)
 #define DT_IW (DT_W + 8)      // 72 staged input columns
 #define DT_IH (DT_H + 8)      // 24 staged input rows
-#define DT_THREADS 256
+#define DT_THREADS 288           // 9 warps: the vertical pass has 72 x 4 = 288 tasks
 #define DT_SMEM_V (CS_LAPLACE_S * DT_H * DT_IW)          // floats
 #define DT_SMEM_DOG ((CS_LAPLACE_S - 1) * DT_H * DT_W)   // floats; the input tile aliases it
 #define DT_SMEM_BYTES ((DT_SMEM_V + DT_SMEM_DOG) * 4)
@@ -48,15 +48,25 @@ __device__ __forceinline__ void dog_tile(const float *__restrict__ img, int w, i
   const int tid = threadIdx.x;
   float *s_in = s_dog;   // alias: the input tile is dead once the vertical pass is done
 
-  for (int i = tid; i < DT_IH * DT_IW; i += DT_THREADS) {
-    int r = i / DT_IW, c = i - r * DT_IW;
-    int gy = min(max(y0 + r - 4, 0), h - 1), gx = min(max(x0 + c - 4, 0), w - 1);
-    s_in[r * DT_IW + c] = __ldg(img + (size_t)gy * pitch + gx);
+  {
+    constexpr int N = (DT_IH * DT_IW) / DT_THREADS;     // 1728 / 288 = 6 loads per thread
+    static_assert(N * DT_THREADS == DT_IH * DT_IW, "tile must divide evenly");
+    float v[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {       // issue every load before the first store: one DRAM round trip
+      int i = tid + DT_THREADS * k;
+      int r = i / DT_IW, c = i - r * DT_IW;
+      int gy = min(max(y0 + r - 4, 0), h - 1), gx = min(max(x0 + c - 4, 0), w - 1);
+      v[k] = __ldg(img + (size_t)gy * pitch + gx);
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) s_in[tid + DT_THREADS * k] = v[k];
   }
   __syncthreads();
 
   // vertical pass: task = (column, group of 4 rows); pair sums are shared by all 8 scales
-  for (int t = tid; t < DT_IW * (DT_H / 4); t += DT_THREADS) {
+  {
+    const int t = tid;
     int g = t / DT_IW, c = t - g * DT_IW;
     float in[12];
 #pragma unroll
@@ -73,8 +83,8 @@ __device__ __forceinline__ void dog_tile(const float *__restrict__ img, int w, i
   }
   __syncthreads();
 
-  // horizontal pass + DoG: thread = (row, 4 consecutive columns), all scales
-  {
+  // horizontal pass + DoG: thread = (row, 4 consecutive columns), all scales (warps 0-7)
+  if (tid < 256) {
     const int r = tid >> 4, c0 = (tid & 15) * 4;
     float prev[4];
 #pragma unroll

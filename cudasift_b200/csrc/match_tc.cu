@@ -6,7 +6,7 @@
 // contraction runs on the 5th-generation tensor cores and only the handful of candidates
 // that can decide a row are re-scored with the reference's sequential FMA chain.
 //
-// Pipeline (4 launches):
+// Pipeline:
 //   1. prep      both descriptor sets -> FP16, written directly in the UMMA "interleaved"
 //                (no-swizzle, K-major) core-matrix layout so that a 256x128 operand tile is
 //                one contiguous 64 KB blob = one cp.async.bulk; row norms for the error bound.
@@ -16,8 +16,9 @@
 //                with tcgen05.ld and keep, per (row, partition), the running maximum.
 //   3. gemm<2>   same GEMM; the epilogue now knows every partition's maximum and emits only
 //                the 4-candidate groups that lie within the error bound of it.
-//   4. resolve   one warp per row: exact k=0..127 FMA chains for the surviving candidates,
-//                then the reference's per-partition update rule and 8-way merge.
+//   (between 2 and 3: bound  -- thread per row: emission thresholds from the pass-1 maxima)
+//   4. chain     thread per surviving candidate: exact k=0..127 FMA chain
+//   5. final     thread per row: the reference's per-partition update rule and 8-way merge.
 // Error bound: |fp16-tensor score - exact chain| <= eps(row) = C1*|a|*max|b| + C2*(|a|+max|b|)
 // (input rounding 2^-11 per operand, FP32 accumulation); every candidate within
 // delta = 2*eps of a maximum that can influence (score, match, ambiguity) is re-scored, so
@@ -37,7 +38,6 @@ namespace cs {
 #define TC_B_BYTES (TC_N * 256)           // 64 KB
 #define TC_STAGES 2
 #define TC_THREADS 384
-#define TC_CAP 16           // candidate groups kept per (row, segment)
 #define TC_PM 12            // floats per (row, segment) of pass-1 output (8 maxima + P0 second)
 #define TC_SMEM_BYTES (TC_A_BYTES + TC_STAGES * TC_B_BYTES + 1024)
 #define TC_C1 1.06e-3f      // > 2^-10 (inputs) + 2^-15 (tensor accumulate) + 2^-17 (reference chain)
@@ -83,8 +83,8 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
                "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-// 32 consecutive 32-bit columns of this thread's TMEM lane
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
+// 32 consecutive 32-bit columns of this thread's TMEM lane (asynchronous: pair with tc_ld_wait)
+__device__ __forceinline__ void tc_ld32_issue(uint32_t taddr, uint32_t (&r)[32])
 {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -94,7 +94,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32])
                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// Wait for the outstanding tcgen05.ld's.  The registers are in/out operands so that the
+// compiler cannot schedule their consumers above the wait.
+__device__ __forceinline__ void tc_ld_wait(uint32_t (&r)[32])
+{
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                 "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                 "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
 }
 
 // UMMA shared-memory descriptor, K-major, no swizzle ("interleaved" core matrices of
@@ -118,11 +128,15 @@ struct TcBuffers {
   float *normA;               // per row of set 1
   float *bmax;                // [0] max norm of set 2 (float bits), [1] bad-input flag
   float *pm;                  // pass-1 maxima  [slot][TC_PM]
-  float4 *cvals;              // pass-2 candidate group values [slot][TC_CAP]
-  unsigned int *cgid;         // pass-2 candidate group ids
-  unsigned int *ccnt;         // pass-2 candidate counts [slot]
+  float *rowthr;              // [row][8] emission thresholds (3e38 = partition cannot matter)
+  int *qhead;                 // [row] head of the row's candidate list (-1 = empty)
+  float4 *qv;                 // candidate queue: the 4 tensor scores of the group
+  float4 *qexact;             // exact chain scores (-1 = not needed)
+  unsigned int *qgid;         // group id (p2 / 4)
+  int *qrow, *qnext;
+  unsigned int qcap;
   int *fbRows;                // fallback row list
-  unsigned int *counters;     // [0] fallback rows, [1] candidates emitted, [2] chains re-scored
+  unsigned int *counters;     // [0] fallback rows, [1] queue entries, [2] chains re-scored, [3] overflow
 };
 
 // ------------------------------------------------------------------------------ prep
@@ -309,70 +323,78 @@ tc_gemm_kernel(const TcPlan pl, const TcBuffers bf)
     const int h = (warp - 4) >> 2, q = warp & 3;
     const int rowInTile = h * TC_M + q * 32 + lane;
     const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + h * TC_N;
-    const float bmax = __int_as_float(*reinterpret_cast<const int *>(bf.bmax));
     float st[8];              // PASS 1: running maxima; PASS 2: emission thresholds
     float t2 = 0.0f;          // PASS 1: second largest group maximum of partition 0
-    unsigned int cnt = 0;
     size_t slot = 0;
+    int row = 0;
     int prevMt = -1, runIdx = 0;
-    for (int u = u_begin, i = 0; u < u_end; u++, i++) {
-      const int mt = u / pl.n_nt, nt = u - mt * pl.n_nt;
-      if (mt != prevMt) {
-        slot = tc_slot(pl, cta, runIdx, rowInTile);
-        prevMt = mt; runIdx++;
-        cnt = 0; t2 = 0.0f;
+    // one 32-column chunk: group j (columns 4j..4j+3) belongs to partition j
+    auto process = [&](const uint32_t (&r)[32], int nt, int c) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]);
+        float v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
+        float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
         if (PASS == 1) {
-#pragma unroll
-          for (int p = 0; p < 8; p++) st[p] = 0.0f;
+          if (j == 0) t2 = fmaxf(t2, fminf(st[0], m));
+          st[j] = fmaxf(st[j], m);
         } else {
-          const int row = mt * TC_MT + rowInTile;
-          RowBound rb;
-          tc_row_bound(pl, bf.pm, mt, rowInTile, row < pl.n1 ? bf.normA[row] : 0.0f, bmax, rb);
-          const float need = tc_pool_second(rb) - rb.delta;   // pool elements below cannot reach (score, ambiguity)
-#pragma unroll
-          for (int p = 0; p < 8; p++) st[p] = (rb.G[p] >= need) ? fmaxf(rb.G[p] - rb.delta, 0.0f) : 3.0e38f;
-          // partition 0 also supplies its SECOND best (quirk Q9): T2 (second largest group maximum)
-          // is a lower bound of that value, so everything above T2 - delta is needed
-          if (rb.G[0] >= need) st[0] = fmaxf(rb.T2 - rb.delta, 0.0f);
-        }
-      }
-      mbar_wait(&bar_acc_full[h], i & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c = 0; c < TC_N / 32; c++) {
-        uint32_t r[32];
-        tc_ld32(tbase + c * 32, r);
-#pragma unroll
-        for (int j = 0; j < 8; j++) {      // group j of this 32-column chunk belongs to partition j
-          float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]);
-          float v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
-          float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-          if (PASS == 1) {
-            if (j == 0) t2 = fmaxf(t2, fminf(st[0], m));
-            st[j] = fmaxf(st[j], m);
-          } else {
-            if (m > st[j]) {
-              if (cnt < TC_CAP) {
-                bf.cvals[slot * TC_CAP + cnt] = make_float4(v0, v1, v2, v3);
-                bf.cgid[slot * TC_CAP + cnt] = (unsigned)(nt * (TC_N / 4) + c * 8 + j);
-              }
-              cnt++;
+          if (m > st[j]) {      // rare: about 3 groups per row over the whole sweep
+            unsigned int idx = atomicAdd(&bf.counters[1], 1u);
+            if (idx < bf.qcap) {
+              bf.qv[idx] = make_float4(v0, v1, v2, v3);
+              bf.qgid[idx] = (unsigned)(nt * (TC_N / 4) + c * 8 + j);
+              bf.qrow[idx] = row;
+              bf.qnext[idx] = atomicExch(&bf.qhead[row], (int)idx);
             }
           }
         }
       }
+    };
+    for (int u = u_begin, i = 0; u < u_end; u++, i++) {
+      const int mt = u / pl.n_nt, nt = u - mt * pl.n_nt;
+      if (mt != prevMt) {
+        slot = tc_slot(pl, cta, runIdx, rowInTile);
+        row = mt * TC_MT + rowInTile;
+        prevMt = mt; runIdx++;
+        t2 = 0.0f;
+        if (PASS == 1) {
+#pragma unroll
+          for (int p = 0; p < 8; p++) st[p] = 0.0f;
+        } else {
+          if (row < pl.n1) {
+            const float4 a = *reinterpret_cast<const float4 *>(bf.rowthr + (size_t)row * 8);
+            const float4 b = *reinterpret_cast<const float4 *>(bf.rowthr + (size_t)row * 8 + 4);
+            st[0] = a.x; st[1] = a.y; st[2] = a.z; st[3] = a.w; st[4] = b.x; st[5] = b.y; st[6] = b.z; st[7] = b.w;
+          } else {
+#pragma unroll
+            for (int p = 0; p < 8; p++) st[p] = 3.0e38f;
+          }
+        }
+      }
+      mbar_wait(&bar_acc_full[h], i & 1);
+      tc_fence_after();
+      // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is reduced
+      uint32_t ra[32], rb[32];
+      tc_ld32_issue(tbase, ra);
+      tc_ld_wait(ra);
+#pragma unroll 1
+      for (int c = 0; c < TC_N / 32; c += 2) {
+        tc_ld32_issue(tbase + (c + 1) * 32, rb);
+        process(ra, nt, c);
+        tc_ld_wait(rb);
+        if (c + 2 < TC_N / 32) tc_ld32_issue(tbase + (c + 2) * 32, ra);
+        process(rb, nt, c + 1);
+        if (c + 2 < TC_N / 32) tc_ld_wait(ra);
+      }
       tc_fence_before();
       mbar_arrive(&bar_acc_empty[h]);
       const bool lastOfRun = (u + 1 == u_end) || ((u + 1) / pl.n_nt != mt);
-      if (lastOfRun) {
-        if (PASS == 1) {
-          float *q4 = bf.pm + slot * TC_PM;
-          *reinterpret_cast<float4 *>(q4) = make_float4(st[0], st[1], st[2], st[3]);
-          *reinterpret_cast<float4 *>(q4 + 4) = make_float4(st[4], st[5], st[6], st[7]);
-          q4[8] = t2;
-        } else {
-          bf.ccnt[slot] = cnt;
-        }
+      if (lastOfRun && PASS == 1) {
+        float *q4 = bf.pm + slot * TC_PM;
+        *reinterpret_cast<float4 *>(q4) = make_float4(st[0], st[1], st[2], st[3]);
+        *reinterpret_cast<float4 *>(q4 + 4) = make_float4(st[4], st[5], st[6], st[7]);
+        q4[8] = t2;
       }
     }
   }
@@ -384,127 +406,117 @@ tc_gemm_kernel(const TcPlan pl, const TcBuffers bf)
   }
 }
 
-// ------------------------------------------------------------------------------ resolve
-#define RS_WARPS 8
-#define RS_MAXC 48          // exact chains per row before falling back
-
-__global__ void __launch_bounds__(RS_WARPS * 32)
-tc_resolve_kernel(const TcPlan pl, const TcBuffers bf, SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ sift2)
+// ------------------------------------------------------------------------------ bound
+// Thread per row: which tensor scores must be re-scored exactly?  Pool = the 8 partition maxima
+// plus partition 0's second best (quirk Q9); only pool elements within delta of the pool's second
+// largest can become (score, ambiguity).  rowthr[p] = smallest tensor score of partition p that
+// still needs an exact chain (3e38: the partition cannot matter).
+__global__ void __launch_bounds__(128)
+tc_bound_kernel(const TcPlan pl, const TcBuffers bf)
 {
-  __shared__ __align__(16) float s_a[RS_WARPS][128];
-  __shared__ int s_p2[RS_WARPS][RS_MAXC];
-  __shared__ float s_sc[RS_WARPS][RS_MAXC];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= pl.n1) return;
+  const int mt = row / TC_MT, rowInTile = row - mt * TC_MT;
   const float bmax = __int_as_float(*reinterpret_cast<const int *>(bf.bmax));
-  for (int row = blockIdx.x * RS_WARPS + warp; row < pl.n1; row += gridDim.x * RS_WARPS) {
-    const int mt = row / TC_MT, rowInTile = row - mt * TC_MT;
-    RowBound rb;
-    tc_row_bound(pl, bf.pm, mt, rowInTile, bf.normA[row], bmax, rb);
-    const float A2 = tc_pool_second(rb);
-    const float need = A2 - rb.delta;
-    float A1 = 0.0f;
+  RowBound rb;
+  tc_row_bound(pl, bf.pm, mt, rowInTile, bf.normA[row], bmax, rb);
+  const float A2 = tc_pool_second(rb);
+  const float need = A2 - rb.delta;
+  float thr[8];
+  // certification: the two pool elements that decide the row must be clearly positive
+  const bool certified = (A2 > 2.0f * rb.delta) && (A2 < 3.0e38f);
 #pragma unroll
-    for (int p = 0; p < 8; p++) A1 = fmaxf(A1, rb.G[p]);
-    // certification: the two pool elements that decide the row must be clearly positive
-    bool fallback = !(A2 > 2.0f * rb.delta) || !(A1 < 3.0e38f);
-    unsigned relevant = 0;
-#pragma unroll
-    for (int p = 0; p < 8; p++) relevant |= (rb.G[p] >= need ? 1u : 0u) << p;
+  for (int p = 0; p < 8; p++)
+    thr[p] = (certified && rb.G[p] >= need) ? fmaxf(rb.G[p] - rb.delta, 0.0f) : 3.0e38f;
+  // partition 0 also supplies its SECOND best: T2 (second largest group maximum) is a lower
+  // bound of that value, so everything above T2 - delta is needed
+  if (certified && rb.G[0] >= need) thr[0] = fmaxf(rb.T2 - rb.delta, 0.0f);
+  *reinterpret_cast<float4 *>(bf.rowthr + (size_t)row * 8) = make_float4(thr[0], thr[1], thr[2], thr[3]);
+  *reinterpret_cast<float4 *>(bf.rowthr + (size_t)row * 8 + 4) = make_float4(thr[4], thr[5], thr[6], thr[7]);
+  if (!certified) bf.fbRows[atomicAdd(&bf.counters[0], 1u)] = row;
+}
 
-    // ---- gather the candidates that need an exact score, in increasing p2 order ----
-    int ncand = 0;
-    const int u0 = mt * pl.n_nt, u1 = u0 + pl.n_nt - 1;
-    for (int c = u0 / pl.U; c <= u1 / pl.U && !fallback; c++) {
-      const int run = mt - (c * pl.U) / pl.n_nt;
-      const size_t slot = tc_slot(pl, c, run, rowInTile);
-      const unsigned cnt = bf.ccnt[slot];
-      if (cnt > TC_CAP) { fallback = true; break; }
-      if (lane == 0) atomicAdd(&bf.counters[1], cnt);
-      // one lane per (entry, member): TC_CAP*4 = 64 -> two rounds
-      for (int base = 0; base < (int)cnt * 4; base += 32) {
-        const int e = (base + lane) >> 2, j = (base + lane) & 3;
-        bool take = false;
-        int p2 = 0;
-        if (e < (int)cnt) {
-          const float4 vv = bf.cvals[slot * TC_CAP + e];
-          const unsigned gid = bf.cgid[slot * TC_CAP + e];
-          const float v = (j == 0 ? vv.x : j == 1 ? vv.y : j == 2 ? vv.z : vv.w);
-          const int part = gid & 7;
-          p2 = (int)gid * 4 + j;
-          float lim = rb.T2;            // partition 0: best and second best are both needed
-#pragma unroll
-          for (int p = 1; p < 8; p++) lim = (part == p ? rb.G[p] : lim);
-          take = ((relevant >> part) & 1u) && (v > fmaxf(lim - rb.delta, 0.0f));
-        }
-        const unsigned mask = __ballot_sync(0xffffffffu, take);
-        const int pos = ncand + __popc(mask & ((1u << lane) - 1));
-        if (take && pos < RS_MAXC) s_p2[warp][pos] = p2;
-        ncand += __popc(mask);
-      }
-    }
-    if (ncand > RS_MAXC) fallback = true;
-    if (fallback) {
-      if (lane == 0) bf.fbRows[atomicAdd(&bf.counters[0], 1u)] = row;
-      continue;
-    }
-    // ---- exact chains: matching.cu:338-351, sequential k = 0..127 from 0 ----
-    __syncwarp();
-    *reinterpret_cast<float4 *>(&s_a[warp][4 * lane]) = __ldg(reinterpret_cast<const float4 *>(sift1[row].data) + lane);
-    __syncwarp();
-    for (int base = 0; base < ncand; base += 32) {
-      const int i = base + lane;
-      if (i < ncand) {
-        const float4 *b = reinterpret_cast<const float4 *>(sift2[s_p2[warp][i]].data);
-        float acc = 0.0f;
+// ------------------------------------------------------------------------------ chain
+// Thread per (queue entry, member): the reference's score, matching.cu:338-351 -- a sequential
+// k = 0..127 FMA chain starting from 0 -- for every candidate that can still decide its row.
+__global__ void __launch_bounds__(256)
+tc_chain_kernel(const TcBuffers bf, const SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ sift2)
+{
+  const unsigned int n = min(bf.counters[1], bf.qcap) * 4u;
+  for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const unsigned int e = t >> 2, j = t & 3;
+    const float4 vv = bf.qv[e];
+    const unsigned int gid = bf.qgid[e];
+    const int row = bf.qrow[e];
+    const float v = (j == 0 ? vv.x : j == 1 ? vv.y : j == 2 ? vv.z : vv.w);
+    float ex = -1.0f;
+    if (v > bf.rowthr[(size_t)row * 8 + (gid & 7)]) {
+      const float4 *a = reinterpret_cast<const float4 *>(sift1[row].data);
+      const float4 *b = reinterpret_cast<const float4 *>(sift2[gid * 4 + j].data);
+      float acc = 0.0f;
 #pragma unroll 8
-        for (int d = 0; d < 32; d++) {
-          const float4 bv = __ldg(b + d);
-          const float4 av = *reinterpret_cast<const float4 *>(&s_a[warp][4 * d]);
-          acc = __fmaf_rn(av.x, bv.x, acc);
-          acc = __fmaf_rn(av.y, bv.y, acc);
-          acc = __fmaf_rn(av.z, bv.z, acc);
-          acc = __fmaf_rn(av.w, bv.w, acc);
-        }
-        s_sc[warp][i] = acc;
+      for (int d = 0; d < 32; d++) {
+        const float4 av = __ldg(a + d), bv = __ldg(b + d);
+        acc = __fmaf_rn(av.x, bv.x, acc);
+        acc = __fmaf_rn(av.y, bv.y, acc);
+        acc = __fmaf_rn(av.z, bv.z, acc);
+        acc = __fmaf_rn(av.w, bv.w, acc);
       }
+      ex = acc;
+      atomicAdd(&bf.counters[2], 1u);
     }
-    __syncwarp();
-    if (lane == 0) {
-      atomicAdd(&bf.counters[2], (unsigned)ncand);
-      // per-partition update rule (matching.cu:354-359) over the exact candidates, p2 ascending
-      float pmx[8], psec0 = 0.0f;
-      int pidx[8];
-#pragma unroll
-      for (int p = 0; p < 8; p++) { pmx[p] = 0.0f; pidx[p] = -1; }
-      for (int i = 0; i < ncand; i++) {
-        const int p2 = s_p2[warp][i];
-        const float sc = s_sc[warp][i];
-        const int part = (p2 >> 2) & 7;
-#pragma unroll
-        for (int p = 0; p < 8; p++)
-          if (p == part) {
-            if (sc > pmx[p]) { if (p == 0) psec0 = pmx[0]; pmx[p] = sc; pidx[p] = p2; }
-            else if (p == 0 && sc > psec0) psec0 = sc;
-          }
-      }
-      // 8-way merge (matching.cu:378-390)
-      float mx = pmx[0], sec = psec0;
-      int idx = pidx[0];
-#pragma unroll
-      for (int y = 0; y < 8; y++)
-        if (idx != pidx[y]) {
-          if (pmx[y] > mx) { sec = fmaxf(mx, sec); mx = pmx[y]; idx = pidx[y]; }
-          else if (pmx[y] > sec) sec = pmx[y];
-        }
-      SiftPoint *o = sift1 + row;
-      o->score = mx;
-      o->match = idx;
-      o->match_xpos = idx >= 0 ? sift2[idx].xpos : 0.0f;
-      o->match_ypos = idx >= 0 ? sift2[idx].ypos : 0.0f;
-      o->ambiguity = __fdiv_rn(sec, __fadd_rn(mx, 1e-6f));
-    }
-    __syncwarp();
+    reinterpret_cast<float *>(bf.qexact)[t] = ex;
   }
+}
+
+// ------------------------------------------------------------------------------ final
+// Thread per row.  The reference's per-partition rule (matching.cu:354-359: strict '>' in
+// increasing p2) is order independent once stated as: pmax = largest score, pidx = lowest p2
+// attaining it, psec = second largest of the multiset; then the 8-way merge of :378-390.
+__global__ void __launch_bounds__(128)
+tc_final_kernel(const TcPlan pl, const TcBuffers bf, SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ sift2)
+{
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= pl.n1) return;
+  float pmx[8], psec0 = 0.0f;
+  int pidx[8];
+#pragma unroll
+  for (int p = 0; p < 8; p++) { pmx[p] = 0.0f; pidx[p] = -1; }
+  if (bf.counters[1] > bf.qcap) atomicMax(&bf.counters[3], 1u);     // queue overflow: redo exactly
+  for (int e = bf.qhead[row]; e >= 0; e = bf.qnext[e]) {
+    const float4 ex = bf.qexact[e];
+    const int p2base = (int)bf.qgid[e] * 4;
+    const int part = (p2base >> 2) & 7;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const float sc = (j == 0 ? ex.x : j == 1 ? ex.y : j == 2 ? ex.z : ex.w);
+      const int p2 = p2base + j;
+      if (!(sc > 0.0f)) continue;          // not needed (-1) or cannot match (matching.cu:317-321)
+#pragma unroll
+      for (int p = 0; p < 8; p++)
+        if (p == part) {
+          if (sc > pmx[p]) { if (p == 0) psec0 = pmx[0]; pmx[p] = sc; pidx[p] = p2; }
+          else {
+            if (sc == pmx[p]) pidx[p] = min(pidx[p], p2);
+            if (p == 0) psec0 = fmaxf(psec0, sc);
+          }
+        }
+    }
+  }
+  float mx = pmx[0], sec = psec0;
+  int idx = pidx[0];
+#pragma unroll
+  for (int y = 0; y < 8; y++)
+    if (idx != pidx[y]) {
+      if (pmx[y] > mx) { sec = fmaxf(mx, sec); mx = pmx[y]; idx = pidx[y]; }
+      else if (pmx[y] > sec) sec = pmx[y];
+    }
+  SiftPoint *o = sift1 + row;
+  o->score = mx;
+  o->match = idx;
+  o->match_xpos = idx >= 0 ? sift2[idx].xpos : 0.0f;
+  o->match_ypos = idx >= 0 ? sift2[idx].ypos : 0.0f;
+  o->ambiguity = __fdiv_rn(sec, __fadd_rn(mx, 1e-6f));
 }
 
 // exact SIMT scan of the rows the tensor path could not certify (match.cu)
@@ -513,9 +525,8 @@ int match_exact_rows(SiftPoint *s1, const SiftPoint *s2, int n2, const int *rows
 
 // ------------------------------------------------------------------------------ host
 struct TcWorkspace {
-  int dev = -1;
   TcBuffers bf = {};
-  size_t capA = 0, capB = 0, capNorm = 0, capPm = 0, capCv = 0, capCg = 0, capCc = 0, capFb = 0;
+  size_t cap[12] = {};
   unsigned int *h_counters = nullptr;
   bool configured = false;
 };
@@ -558,19 +569,27 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
   pl.grid = idivup(pl.total, pl.U);
   pl.runs = idivup(pl.U, pl.n_nt) + 1;
   const size_t slots = (size_t)pl.grid * pl.runs * TC_MT;
+  const size_t rowsPad = (size_t)pl.n_mt * TC_MT;
+  const unsigned int qcap = (unsigned int)(16 * rowsPad + 65536);
+  TcBuffers &bf = ws.bf;
   int r;
-  if ((r = ensure((void **)&ws.bf.a16, &ws.capA, (size_t)pl.n_mt * TC_A_BYTES)) < 0) return r;
-  if ((r = ensure((void **)&ws.bf.b16, &ws.capB, (size_t)pl.n_nt * TC_B_BYTES)) < 0) return r;
-  if ((r = ensure((void **)&ws.bf.normA, &ws.capNorm, (size_t)pl.n_mt * TC_MT * sizeof(float))) < 0) return r;
-  if ((r = ensure((void **)&ws.bf.pm, &ws.capPm, slots * TC_PM * sizeof(float))) < 0) return r;
-  if ((r = ensure((void **)&ws.bf.cvals, &ws.capCv, slots * TC_CAP * sizeof(float4))) < 0) return r;
-  if ((r = ensure((void **)&ws.bf.cgid, &ws.capCg, slots * TC_CAP * sizeof(unsigned))) < 0) return r;
-  if ((r = ensure((void **)&ws.bf.ccnt, &ws.capCc, slots * sizeof(unsigned))) < 0) return r;
-  if ((r = ensure((void **)&ws.bf.fbRows, &ws.capFb, (size_t)pl.n_mt * TC_MT * sizeof(int))) < 0) return r;
-  if (!ws.bf.bmax) {
+  if ((r = ensure((void **)&bf.a16, &ws.cap[0], (size_t)pl.n_mt * TC_A_BYTES)) < 0) return r;
+  if ((r = ensure((void **)&bf.b16, &ws.cap[1], (size_t)pl.n_nt * TC_B_BYTES)) < 0) return r;
+  if ((r = ensure((void **)&bf.normA, &ws.cap[2], rowsPad * sizeof(float))) < 0) return r;
+  if ((r = ensure((void **)&bf.pm, &ws.cap[3], slots * TC_PM * sizeof(float))) < 0) return r;
+  if ((r = ensure((void **)&bf.rowthr, &ws.cap[4], rowsPad * 8 * sizeof(float))) < 0) return r;
+  if ((r = ensure((void **)&bf.qhead, &ws.cap[5], rowsPad * sizeof(int))) < 0) return r;
+  if ((r = ensure((void **)&bf.qv, &ws.cap[6], (size_t)qcap * sizeof(float4))) < 0) return r;
+  if ((r = ensure((void **)&bf.qexact, &ws.cap[7], (size_t)qcap * sizeof(float4))) < 0) return r;
+  if ((r = ensure((void **)&bf.qgid, &ws.cap[8], (size_t)qcap * sizeof(unsigned))) < 0) return r;
+  if ((r = ensure((void **)&bf.qrow, &ws.cap[9], (size_t)qcap * sizeof(int))) < 0) return r;
+  if ((r = ensure((void **)&bf.qnext, &ws.cap[10], (size_t)qcap * sizeof(int))) < 0) return r;
+  if ((r = ensure((void **)&bf.fbRows, &ws.cap[11], rowsPad * sizeof(int))) < 0) return r;
+  bf.qcap = qcap;
+  if (!bf.bmax) {
     size_t dummy = 0;
-    if ((r = ensure((void **)&ws.bf.bmax, &dummy, 64)) < 0) return r;
-    ws.bf.counters = reinterpret_cast<unsigned int *>(ws.bf.bmax) + 4;
+    if ((r = ensure((void **)&bf.bmax, &dummy, 64)) < 0) return r;
+    bf.counters = reinterpret_cast<unsigned int *>(bf.bmax) + 4;
     CS_CUDA(cudaMallocHost((void **)&ws.h_counters, 64));
   }
   if (!ws.configured) {
@@ -578,19 +597,22 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
     CS_CUDA(cudaFuncSetAttribute(tc_gemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
     ws.configured = true;
   }
-  CS_CUDA(cudaMemsetAsync(ws.bf.bmax, 0, 64, st));
-  tc_prep_kernel<<<pl.n_mt * (TC_MT / 32), 512, 0, st>>>(s1, n1, TC_M, ws.bf.a16, ws.bf.normA, ws.bf.bmax, 0);
-  tc_prep_kernel<<<pl.n_nt * (TC_N / 32), 512, 0, st>>>(s2, n2v, TC_N, ws.bf.b16, nullptr, ws.bf.bmax, 1);
-  tc_gemm_kernel<1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(pl, ws.bf);
-  tc_gemm_kernel<2><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(pl, ws.bf);
-  tc_resolve_kernel<<<sms * 4, RS_WARPS * 32, 0, st>>>(pl, ws.bf, s1, s2);
-  count_launch(5);
+  CS_CUDA(cudaMemsetAsync(bf.bmax, 0, 64, st));
+  CS_CUDA(cudaMemsetAsync(bf.qhead, 0xFF, (size_t)n1 * sizeof(int), st));
+  tc_prep_kernel<<<pl.n_mt * (TC_MT / 32), 512, 0, st>>>(s1, n1, TC_M, bf.a16, bf.normA, bf.bmax, 0);
+  tc_prep_kernel<<<pl.n_nt * (TC_N / 32), 512, 0, st>>>(s2, n2v, TC_N, bf.b16, nullptr, bf.bmax, 1);
+  tc_gemm_kernel<1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(pl, bf);
+  tc_bound_kernel<<<idivup(n1, 128), 128, 0, st>>>(pl, bf);
+  tc_gemm_kernel<2><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(pl, bf);
+  tc_chain_kernel<<<sms * 2, 256, 0, st>>>(bf, s1, s2);
+  tc_final_kernel<<<idivup(n1, 128), 128, 0, st>>>(pl, bf, s1, s2);
+  count_launch(7);
   CS_CUDA(cudaGetLastError());
-  if ((r = match_exact_rows(s1, s2, n2, ws.bf.fbRows, ws.bf.counters, st)) < 0) return r;
-  // bad inputs (|x| >= 32768, NaN, Inf) cannot be bounded in FP16: redo everything exactly
-  CS_CUDA(cudaMemcpyAsync(ws.h_counters, ws.bf.bmax, 64, cudaMemcpyDeviceToHost, st));
+  if ((r = match_exact_rows(s1, s2, n2, bf.fbRows, bf.counters, st)) < 0) return r;
+  // inputs FP16 cannot bound (|x| >= 32768, NaN, Inf) or a queue overflow: redo everything exactly
+  CS_CUDA(cudaMemcpyAsync(ws.h_counters, bf.bmax, 64, cudaMemcpyDeviceToHost, st));
   CS_CUDA(cudaStreamSynchronize(st));
-  if (ws.h_counters[1] != 0) return match_exact(s1, n1, s2, n2, st);
+  if (ws.h_counters[1] != 0 || ws.h_counters[4 + 3] != 0) return match_exact(s1, n1, s2, n2, st);
   stats[0] = ws.h_counters[4 + 1];
   stats[1] = ws.h_counters[4 + 2];
   stats[2] = ws.h_counters[4 + 0];

@@ -44,11 +44,23 @@ lowpass_kernel(const float *__restrict__ src, int srcPitch, float *__restrict__ 
   const int tid = threadIdx.x;
   const int x0 = blockIdx.x * LP_W, y0 = blockIdx.y * LP_H;
 
-  // stage the input tile (+halo), clamped
-  for (int i = tid; i < LP_IH * LP_IW; i += 256) {
-    int r = i / LP_IW, c = i - r * LP_IW;
-    int gy = clampi(y0 + r - LP_R, 0, h - 1), gx = clampi(x0 + c - LP_R, 0, w - 1);
-    s_in[r][c] = __ldg(src + (size_t)gy * srcPitch + gx);
+  // stage the input tile (+halo), clamped.  All loads of a thread are issued before the
+  // first shared-memory store so that their DRAM latencies overlap (one round trip, not 22).
+  {
+    constexpr int N = (LP_IH * LP_IW + 255) / 256;
+    float v[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      int i = tid + 256 * k;
+      int r = i / LP_IW, c = i - r * LP_IW;
+      int gy = clampi(y0 + r - LP_R, 0, h - 1), gx = clampi(x0 + c - LP_R, 0, w - 1);
+      v[k] = (i < LP_IH * LP_IW) ? __ldg(src + (size_t)gy * srcPitch + gx) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      int i = tid + 256 * k;
+      if (i < LP_IH * LP_IW) (&s_in[0][0])[i] = v[k];
+    }
   }
   __syncthreads();
 
@@ -127,10 +139,21 @@ scaledown_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, 
   const int ox0 = blockIdx.x * SD_W, oy0 = blockIdx.y * SD_H;   // output-space origin
   const int w2 = w / 2, h2 = h / 2;
 
-  for (int i = tid; i < SD_IH * SD_IW; i += 256) {
-    int r = i / SD_IW, c = i - r * SD_IW;
-    int gy = clampi(2 * oy0 + r - 2, 0, h - 1), gx = clampi(2 * ox0 + c - 2, 0, w - 1);
-    s_in[r][c] = __ldg(src + (size_t)gy * pitch + gx);
+  {
+    constexpr int N = (SD_IH * SD_IW + 255) / 256;
+    float v[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {       // all loads first: one DRAM round trip per thread
+      int i = tid + 256 * k;
+      int r = i / SD_IW, c = i - r * SD_IW;
+      int gy = clampi(2 * oy0 + r - 2, 0, h - 1), gx = clampi(2 * ox0 + c - 2, 0, w - 1);
+      v[k] = (i < SD_IH * SD_IW) ? __ldg(src + (size_t)gy * pitch + gx) : 0.0f;
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      int i = tid + 256 * k;
+      if (i < SD_IH * SD_IW) (&s_in[0][0])[i] = v[k];
+    }
   }
   __syncthreads();
 
