@@ -7,8 +7,10 @@
 // summation order -- and therefore the low-order bits of every descriptor -- change from
 // run to run.  Here a single launch serves all octaves: one 128-thread CTA per keypoint
 // computes the orientation histogram, its one or two peaks, and then one descriptor per
-// peak.  Both histograms are accumulated by an owner-computes gather in a fixed order
-// (the same order oracle/sift_oracle.c uses), so results are run-to-run deterministic.
+// peak.  Both histograms are accumulated without atomics in a fixed order (private partial
+// histograms in shared memory, then a fixed-order reduction), so results are run-to-run
+// deterministic; the summation order differs from the reference's only as much as the
+// reference's own order differs between two of its runs.
 //
 // Image samples go through the texture unit exactly as in the reference (bilinear,
 // clamp, unnormalised coordinates, cudaSiftH.cu:186-205), so the 1.8 fixed-point
@@ -38,7 +40,6 @@ __device__ __forceinline__ float fast_atan2(float y, float x)
 __global__ void __launch_bounds__(DS_THREADS)
 describe_kernel(const __grid_constant__ DescribeParams P)
 {
-  __shared__ float s_hist[64];
   __shared__ float s_gauss11[11];
   __shared__ float s_gauss16[16];
   __shared__ float s_ow[121];          // orientation sample weights
@@ -46,7 +47,8 @@ describe_kernel(const __grid_constant__ DescribeParams P)
   __shared__ __align__(16) float s_g2[256][4];   // descriptor votes per sample: ul, ll, ur, lr
   __shared__ float s_angf[256];
   __shared__ int s_angi[256];
-  __shared__ float s_buf[128];
+  __shared__ float s_hp[32][33];       // orientation: private 32-bin histograms of warp 0's lanes
+  __shared__ float s_pb[128][9];       // descriptor: private angle bins (+ Q22 overflow slot) per (cell, row)
   __shared__ float s_sums[4];
   __shared__ float s_ori[2];
   __shared__ int s_slot[2];
@@ -54,6 +56,7 @@ describe_kernel(const __grid_constant__ DescribeParams P)
 
   const int tx = threadIdx.x;
   if (tx < 16) s_gauss16[tx] = __expf(-(tx - 7.5f) * (tx - 7.5f) / 128.0f);   // cudaSiftD.cu:318
+  for (int i = tx; i < 32 * 33; i += DS_THREADS) (&s_hp[0][0])[i] = 0.0f;
 
   const unsigned int found = P.counters[0];
   const int numPrim = (int)min(found, (unsigned)P.maxPts);
@@ -71,7 +74,6 @@ describe_kernel(const __grid_constant__ DescribeParams P)
         float t = (float)(tx - 5);
         s_gauss11[tx] = expf(__fmul_rn(t, __fmul_rn(t, i2sigma2)));                     // :984
       }
-      if (tx < 64) s_hist[tx] = 0.0f;
     }
     __syncthreads();
     if (tx < 121) {
@@ -88,56 +90,73 @@ describe_kernel(const __grid_constant__ DescribeParams P)
       s_obin[tx] = bin;
     }
     __syncthreads();
-    if (tx < 32) {   // owner-computes gather in sample order (deterministic)
-      float acc = 0.0f;
-      for (int i = 0; i < 121; i++)
-        if (s_obin[i] == tx) acc = __fadd_rn(acc, s_ow[i]);
-      s_hist[tx] = acc;
-    }
-    __syncthreads();
-    const int x1m = (tx >= 1 ? tx - 1 : tx + 31), x1p = (tx <= 30 ? tx + 1 : tx - 31);
-    if (tx < 32) {   // :1004-1010
-      int x2m = (tx >= 2 ? tx - 2 : tx + 30), x2p = (tx <= 29 ? tx + 2 : tx - 30);
-      float v = __fmaf_rn(s_hist[tx], 6.0f, __fmul_rn(4.0f, __fadd_rn(s_hist[x1m], s_hist[x1p])));
-      s_hist[tx + 32] = __fadd_rn(v, __fadd_rn(s_hist[x2m], s_hist[x2p]));
-    }
-    __syncthreads();
-    if (tx < 32) {   // :1012-1015
-      float v = s_hist[32 + tx];
-      s_hist[tx] = (v > s_hist[32 + x1m] && v >= s_hist[32 + x1p] ? v : 0.0f);
-    }
-    __syncthreads();
-    if (tx == 0) {   // :1017-1053
-      float maxval1 = 0.0f, maxval2 = 0.0f;
-      int i1 = -1, i2 = -1;
-      for (int i = 0; i < 32; i++) {
-        float v = s_hist[i];
-        if (v > maxval1) { maxval2 = maxval1; maxval1 = v; i2 = i1; i1 = i; }
-        else if (v > maxval2) { maxval2 = v; i2 = i; }
-      }
-      float val1 = s_hist[32 + ((i1 + 1) & 31)], val2 = s_hist[32 + ((i1 + 31) & 31)];
-      float peak = __fadd_rn((float)i1, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(val1, val2)),
-                                                  __fsub_rn(__fsub_rn(__fadd_rn(maxval1, maxval1), val1), val2)));
-      s_ori[0] = __fmul_rn(11.25f, (peak < 0.0f ? __fadd_rn(peak, 32.0f) : peak));
-      s_slot[0] = pt;
-      int nori = 1;
-      if (maxval2 > __fmul_rn(0.8f, maxval1)) {
-        float v1 = s_hist[32 + ((i2 + 1) & 31)], v2 = s_hist[32 + ((i2 + 31) & 31)];
-        float pk = __fadd_rn((float)i2, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(v1, v2)),
-                                                  __fsub_rn(__fsub_rn(__fadd_rn(maxval2, maxval2), v1), v2)));
-        // Reference quirk Q1 (cudaSiftH.cu:115): secondary orientations of the finest
-        // octave land beyond numPts and are never reported -> do not produce them.
-        if (psub != P.finestSubsampling) {
-          atomicMax(&P.counters[1], (unsigned)numPrim);
-          unsigned int idx = atomicAdd(&P.counters[1], 1u);
-          if (idx < (unsigned)P.maxPts) {
-            s_ori[1] = __fmul_rn(11.25f, (pk < 0.0f ? __fadd_rn(pk, 32.0f) : pk));
-            s_slot[1] = (int)idx;
-            nori = 2;
-          }
+    if (tx < 32) {
+      // warp 0: lane l accumulates samples l, l+32, l+64, l+96 into its private histogram, then
+      // lane b sums column b over the 32 lanes in lane order (fixed order, no atomics)
+      int touched[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int i = tx + 32 * k;
+        touched[k] = -1;
+        if (i < 121) {
+          const int b = s_obin[i];
+          s_hp[tx][b] = __fadd_rn(s_hp[tx][b], s_ow[i]);
+          touched[k] = b;
         }
       }
-      s_nori = nori;
+      __syncwarp();
+      float acc = 0.0f;
+#pragma unroll 8
+      for (int l = 0; l < 32; l++) acc = __fadd_rn(acc, s_hp[l][tx]);
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (touched[k] >= 0) s_hp[tx][touched[k]] = 0.0f;
+      // :1004-1010 circular [1 4 6 4 1] smoothing, lane = bin
+      const float h0 = acc;
+      const float h1m = __shfl_sync(0xffffffffu, h0, (tx + 31) & 31), h1p = __shfl_sync(0xffffffffu, h0, (tx + 1) & 31);
+      const float h2m = __shfl_sync(0xffffffffu, h0, (tx + 30) & 31), h2p = __shfl_sync(0xffffffffu, h0, (tx + 2) & 31);
+      const float sm = __fadd_rn(__fmaf_rn(h0, 6.0f, __fmul_rn(4.0f, __fadd_rn(h1m, h1p))), __fadd_rn(h2m, h2p));
+      const float smm = __shfl_sync(0xffffffffu, sm, (tx + 31) & 31), smp = __shfl_sync(0xffffffffu, sm, (tx + 1) & 31);
+      const float pk = (sm > smm && sm >= smp ? sm : 0.0f);       // :1012-1015
+      // :1018-1033: the serial scan keeps (largest, its first index) and (largest of the rest, its
+      // first index); stated order-independently and evaluated with warp votes
+      float m1 = pk;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+      const unsigned b1 = __ballot_sync(0xffffffffu, pk == m1);
+      const int i1 = (m1 > 0.0f) ? (__ffs(b1) - 1) : -1;
+      float rest = (tx == i1) ? 0.0f : pk, m2 = rest;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m2 = fmaxf(m2, __shfl_xor_sync(0xffffffffu, m2, o));
+      const unsigned b2 = __ballot_sync(0xffffffffu, rest == m2 && tx != i1);
+      const int i2 = (m2 > 0.0f) ? (__ffs(b2) - 1) : -1;
+      const float maxval1 = (i1 >= 0) ? m1 : 0.0f, maxval2 = (i2 >= 0) ? m2 : 0.0f;
+      const float val1 = __shfl_sync(0xffffffffu, sm, (i1 + 1) & 31), val2 = __shfl_sync(0xffffffffu, sm, (i1 + 31) & 31);
+      const float v1 = __shfl_sync(0xffffffffu, sm, (i2 + 1) & 31), v2 = __shfl_sync(0xffffffffu, sm, (i2 + 31) & 31);
+      if (tx == 0) {   // :1034-1053
+        float peak = __fadd_rn((float)i1, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(val1, val2)),
+                                                    __fsub_rn(__fsub_rn(__fadd_rn(maxval1, maxval1), val1), val2)));
+        s_ori[0] = __fmul_rn(11.25f, (peak < 0.0f ? __fadd_rn(peak, 32.0f) : peak));
+        s_slot[0] = pt;
+        int nori = 1;
+        if (maxval2 > __fmul_rn(0.8f, maxval1)) {
+          float pk2 = __fadd_rn((float)i2, __fdiv_rn(__fmul_rn(0.5f, __fsub_rn(v1, v2)),
+                                                     __fsub_rn(__fsub_rn(__fadd_rn(maxval2, maxval2), v1), v2)));
+          // Reference quirk Q1 (cudaSiftH.cu:115): secondary orientations of the finest
+          // octave land beyond numPts and are never reported -> do not produce them.
+          if (psub != P.finestSubsampling) {
+            atomicMax(&P.counters[1], (unsigned)numPrim);
+            unsigned int idx = atomicAdd(&P.counters[1], 1u);
+            if (idx < (unsigned)P.maxPts) {
+              s_ori[1] = __fmul_rn(11.25f, (pk2 < 0.0f ? __fadd_rn(pk2, 32.0f) : pk2));
+              s_slot[1] = (int)idx;
+              nori = 2;
+            }
+          }
+        }
+        s_nori = nori;
+      }
     }
     __syncthreads();
     const int nori = s_nori;
@@ -149,7 +168,6 @@ describe_kernel(const __grid_constant__ DescribeParams P)
       float sina = __sinf(theta), cosa = __cosf(theta);
       float scale = __fmul_rn(12.0f / 16.0f, pscale);
       float ssina = __fmul_rn(scale, sina), scosa = __fmul_rn(scale, cosa);
-      int has8 = 0;
 #pragma unroll
       for (int rep = 0; rep < 2; rep++) {
         const int sidx = tx + rep * DS_THREADS;     // sample index = y*16 + x
@@ -173,54 +191,53 @@ describe_kernel(const __grid_constant__ DescribeParams P)
         angf = __fsub_rn(angf, (float)angi);
         // Quirk Q22: for dy == +0, dx < 0 (edges of saturated areas) angf = 8.0001 and angi = 8;
         // the reference then adds its "iangf" vote at flat index 8*cell + 8, i.e. into angle
-        // bin 0 of the NEXT cell (cudaSiftD.cu:353-384).  Reproduced below (has8 path).
-        has8 |= (angi >= 8);
+        // bin 0 of the NEXT cell (cudaSiftD.cu:353-384).  Reproduced in the accumulation below.
         float gl = __fmul_rn(ihorf, grad), gr = __fmul_rn(horf, grad);
         float4 g2 = make_float4(__fmul_rn(iverf, gl), __fmul_rn(verf, gl), __fmul_rn(iverf, gr), __fmul_rn(verf, gr));
         *reinterpret_cast<float4 *>(s_g2[sidx]) = g2;
         s_angf[sidx] = angf;
         s_angi[sidx] = angi;
       }
-      has8 = __syncthreads_or(has8);
-      {  // owner-computes gather: thread = output bin (ycell, xcell, angle)
-        const int cy = tx >> 5, cx = (tx >> 3) & 3, a = tx & 7;
-        const int ylo = max(0, 4 * cy - 2), yhi = min(15, 4 * cy + 5);
-        const int xlo = max(0, 4 * cx - 2), xhi = min(15, 4 * cx + 5);
-        float acc = 0.0f;
-        for (int y = ylo; y <= yhi; y++) {
+      __syncthreads();
+      {  // deterministic accumulation.  Thread (cell, k): the k-th sample row of the cell's 8x8
+         // window, summed over x into 8 private angle bins (+ slot 8 for quirk Q22: angi == 8
+         // votes into angle bin 0 of the NEXT cell in flat order, cudaSiftD.cu:353-384).
+        const int cell = tx >> 3, kr = tx & 7;
+        const int cy = cell >> 2, cx = cell & 3;
+        float *pb = s_pb[tx];
+#pragma unroll
+        for (int a = 0; a < 9; a++) pb[a] = 0.0f;
+        const int y = 4 * cy - 2 + kr;
+        if (y >= 0 && y <= 15) {
           const int lower = (((y + 2) >> 2) - 1 != cy);       // sample votes into its lower cell
+          const int xlo = max(0, 4 * cx - 2), xhi = min(15, 4 * cx + 5);
           for (int x = xlo; x <= xhi; x++) {
             const int right = (((x + 2) >> 2) - 1 != cx);     // ... into its right cell
             const int sidx = y * 16 + x;
             const int angi = s_angi[sidx];
             const int angp = (angi < 7 ? angi + 1 : 0);
-            if (angi == a || angp == a) {
-              float g2 = s_g2[sidx][2 * right + lower];
-              float af = s_angf[sidx];
-              float wgt = (angi == a ? __fsub_rn(1.0f, af) : af);
-              acc = __fadd_rn(acc, __fmul_rn(wgt, g2));
-            }
+            const float af = s_angf[sidx];
+            const float g2 = s_g2[sidx][2 * right + lower];
+            const int a1 = min(angi, 8);
+            pb[a1] = __fadd_rn(pb[a1], __fmul_rn(__fsub_rn(1.0f, af), g2));
+            pb[angp] = __fadd_rn(pb[angp], __fmul_rn(af, g2));
           }
         }
-        if (has8 && a == 0 && tx >= 8) {
-          // Q22 votes of the previous cell (flat order) land in this cell's bin 0
-          const int pc = (tx >> 3) - 1, pcy = pc >> 2, pcx = pc & 3;
-          const int y0 = max(0, 4 * pcy - 2), y1 = min(15, 4 * pcy + 5);
-          const int x0 = max(0, 4 * pcx - 2), x1 = min(15, 4 * pcx + 5);
-          for (int y = y0; y <= y1; y++) {
-            const int lower = (((y + 2) >> 2) - 1 != pcy);
-            for (int x = x0; x <= x1; x++) {
-              const int right = (((x + 2) >> 2) - 1 != pcx);
-              const int sidx = y * 16 + x;
-              if (s_angi[sidx] >= 8)
-                acc = __fadd_rn(acc, __fmul_rn(__fsub_rn(1.0f, s_angf[sidx]), s_g2[sidx][2 * right + lower]));
-            }
-          }
+      }
+      __syncthreads();
+      float v;
+      {  // thread = output bin (cell, angle): fixed-order sum over the 8 rows
+        const int cell = tx >> 3, a = tx & 7;
+        float acc = 0.0f;
+#pragma unroll
+        for (int r = 0; r < 8; r++) acc = __fadd_rn(acc, s_pb[cell * 8 + r][a]);
+        if (a == 0 && cell > 0) {
+#pragma unroll
+          for (int r = 0; r < 8; r++) acc = __fadd_rn(acc, s_pb[(cell - 1) * 8 + r][8]);
         }
-        s_buf[tx] = acc;
+        v = acc;
       }
       // :391-409 normalise, clamp at 0.2, renormalise
-      float v = s_buf[tx];
       float sum = __fmul_rn(v, v);
 #pragma unroll
       for (int i = 16; i > 0; i /= 2) sum = __fadd_rn(sum, __shfl_down_sync(0xffffffffu, sum, i));

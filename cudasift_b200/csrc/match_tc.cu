@@ -38,6 +38,7 @@ namespace cs {
 #define TC_B_BYTES (TC_N * 256)           // 64 KB
 #define TC_STAGES 2
 #define TC_THREADS 384
+#define TC_RT 16            // exact scores kept per row before falling back
 #define TC_PM 12            // floats per (row, segment) of pass-1 output (8 maxima + P0 second)
 #define TC_SMEM_BYTES (TC_A_BYTES + TC_STAGES * TC_B_BYTES + 1024)
 #define TC_C1 1.06e-3f      // > 2^-10 (inputs) + 2^-15 (tensor accumulate) + 2^-17 (reference chain)
@@ -122,6 +123,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 // ------------------------------------------------------------------------------ workspace
 struct TcPlan {
   int n1, n2v, n_mt, n_nt, total, U, runs, grid;
+  int dbg;   // experiments (env CS_TC_DBG): 1 = do not reload B tiles, 2 = split bulk copies into 8 KB pieces
 };
 struct TcBuffers {
   __half *a16, *b16;          // packed operand tiles
@@ -129,12 +131,12 @@ struct TcBuffers {
   float *bmax;                // [0] max norm of set 2 (float bits), [1] bad-input flag
   float *pm;                  // pass-1 maxima  [slot][TC_PM]
   float *rowthr;              // [row][8] emission thresholds (3e38 = partition cannot matter)
-  int *qhead;                 // [row] head of the row's candidate list (-1 = empty)
   float4 *qv;                 // candidate queue: the 4 tensor scores of the group
-  float4 *qexact;             // exact chain scores (-1 = not needed)
   unsigned int *qgid;         // group id (p2 / 4)
-  int *qrow, *qnext;
+  int *qrow;
   unsigned int qcap;
+  unsigned int *rcnt;         // [row] number of exact scores in the row's table
+  float2 *rtab;               // [row][TC_RT] (exact score, p2 as int bits)
   int *fbRows;                // fallback row list
   unsigned int *counters;     // [0] fallback rows, [1] queue entries, [2] chains re-scored, [3] overflow
 };
@@ -284,9 +286,17 @@ tc_gemm_kernel(const TcPlan pl, const TcBuffers bf)
         }
         const int s = i % TC_STAGES, it = i / TC_STAGES;
         if (it > 0) mbar_wait(&bar_b_empty[s], (it - 1) & 1);
-        mbar_expect_tx(&bar_b_full[s], TC_B_BYTES);
-        bulk_g2s(sB + s * TC_B_BYTES, reinterpret_cast<const uint8_t *>(bf.b16) + (size_t)nt * TC_B_BYTES, TC_B_BYTES,
-                 &bar_b_full[s]);
+        const uint8_t *srcB = reinterpret_cast<const uint8_t *>(bf.b16) + (size_t)nt * TC_B_BYTES;
+        if ((pl.dbg & 1) && it > 0) {
+          mbar_arrive(&bar_b_full[s]);                  // experiment: MMA/epilogue rate without B traffic
+        } else if (pl.dbg & 2) {
+          mbar_expect_tx(&bar_b_full[s], TC_B_BYTES);
+          for (int piece = 0; piece < 8; piece++)
+            bulk_g2s(sB + s * TC_B_BYTES + piece * 8192, srcB + piece * 8192, 8192, &bar_b_full[s]);
+        } else {
+          mbar_expect_tx(&bar_b_full[s], TC_B_BYTES);
+          bulk_g2s(sB + s * TC_B_BYTES, srcB, TC_B_BYTES, &bar_b_full[s]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -345,7 +355,6 @@ tc_gemm_kernel(const TcPlan pl, const TcBuffers bf)
               bf.qv[idx] = make_float4(v0, v1, v2, v3);
               bf.qgid[idx] = (unsigned)(nt * (TC_N / 4) + c * 8 + j);
               bf.qrow[idx] = row;
-              bf.qnext[idx] = atomicExch(&bf.qhead[row], (int)idx);
             }
           }
         }
@@ -439,22 +448,23 @@ tc_bound_kernel(const TcPlan pl, const TcBuffers bf)
 // ------------------------------------------------------------------------------ chain
 // Thread per (queue entry, member): the reference's score, matching.cu:338-351 -- a sequential
 // k = 0..127 FMA chain starting from 0 -- for every candidate that can still decide its row.
+// Results go to the row's small table (slot by atomic counter; order is irrelevant, see final).
 __global__ void __launch_bounds__(256)
 tc_chain_kernel(const TcBuffers bf, const SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ sift2)
 {
   const unsigned int n = min(bf.counters[1], bf.qcap) * 4u;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && bf.counters[1] > bf.qcap) atomicMax(&bf.counters[3], 1u);
   for (unsigned int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const unsigned int e = t >> 2, j = t & 3;
     const float4 vv = bf.qv[e];
     const unsigned int gid = bf.qgid[e];
     const int row = bf.qrow[e];
     const float v = (j == 0 ? vv.x : j == 1 ? vv.y : j == 2 ? vv.z : vv.w);
-    float ex = -1.0f;
     if (v > bf.rowthr[(size_t)row * 8 + (gid & 7)]) {
       const float4 *a = reinterpret_cast<const float4 *>(sift1[row].data);
       const float4 *b = reinterpret_cast<const float4 *>(sift2[gid * 4 + j].data);
       float acc = 0.0f;
-#pragma unroll 8
+#pragma unroll 16
       for (int d = 0; d < 32; d++) {
         const float4 av = __ldg(a + d), bv = __ldg(b + d);
         acc = __fmaf_rn(av.x, bv.x, acc);
@@ -462,10 +472,10 @@ tc_chain_kernel(const TcBuffers bf, const SiftPoint *__restrict__ sift1, const S
         acc = __fmaf_rn(av.z, bv.z, acc);
         acc = __fmaf_rn(av.w, bv.w, acc);
       }
-      ex = acc;
+      const unsigned int slot = atomicAdd(&bf.rcnt[row], 1u);
+      if (slot < TC_RT) bf.rtab[(size_t)row * TC_RT + slot] = make_float2(acc, __int_as_float((int)(gid * 4 + j)));
       atomicAdd(&bf.counters[2], 1u);
     }
-    reinterpret_cast<float *>(bf.qexact)[t] = ex;
   }
 }
 
@@ -473,7 +483,7 @@ tc_chain_kernel(const TcBuffers bf, const SiftPoint *__restrict__ sift1, const S
 // Thread per row.  The reference's per-partition rule (matching.cu:354-359: strict '>' in
 // increasing p2) is order independent once stated as: pmax = largest score, pidx = lowest p2
 // attaining it, psec = second largest of the multiset; then the 8-way merge of :378-390.
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(64)
 tc_final_kernel(const TcPlan pl, const TcBuffers bf, SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ sift2)
 {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -482,26 +492,27 @@ tc_final_kernel(const TcPlan pl, const TcBuffers bf, SiftPoint *__restrict__ sif
   int pidx[8];
 #pragma unroll
   for (int p = 0; p < 8; p++) { pmx[p] = 0.0f; pidx[p] = -1; }
-  if (bf.counters[1] > bf.qcap) atomicMax(&bf.counters[3], 1u);     // queue overflow: redo exactly
-  for (int e = bf.qhead[row]; e >= 0; e = bf.qnext[e]) {
-    const float4 ex = bf.qexact[e];
-    const int p2base = (int)bf.qgid[e] * 4;
-    const int part = (p2base >> 2) & 7;
+  const unsigned int n = bf.rcnt[row];
+  if (n > TC_RT) {      // more near-ties than the table holds: exact scan of this row instead
+    bf.fbRows[atomicAdd(&bf.counters[0], 1u)] = row;
+    return;
+  }
+  const float2 *tab = bf.rtab + (size_t)row * TC_RT;
+  for (unsigned int i = 0; i < n; i++) {
+    const float2 en = tab[i];
+    const float sc = en.x;
+    const int p2 = __float_as_int(en.y);
+    const int part = (p2 >> 2) & 7;
+    if (!(sc > 0.0f)) continue;            // cannot match (matching.cu:317-321)
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const float sc = (j == 0 ? ex.x : j == 1 ? ex.y : j == 2 ? ex.z : ex.w);
-      const int p2 = p2base + j;
-      if (!(sc > 0.0f)) continue;          // not needed (-1) or cannot match (matching.cu:317-321)
-#pragma unroll
-      for (int p = 0; p < 8; p++)
-        if (p == part) {
-          if (sc > pmx[p]) { if (p == 0) psec0 = pmx[0]; pmx[p] = sc; pidx[p] = p2; }
-          else {
-            if (sc == pmx[p]) pidx[p] = min(pidx[p], p2);
-            if (p == 0) psec0 = fmaxf(psec0, sc);
-          }
+    for (int p = 0; p < 8; p++)
+      if (p == part) {
+        if (sc > pmx[p]) { if (p == 0) psec0 = pmx[0]; pmx[p] = sc; pidx[p] = p2; }
+        else {
+          if (sc == pmx[p]) pidx[p] = min(pidx[p], p2);
+          if (p == 0) psec0 = fmaxf(psec0, sc);
         }
-    }
+      }
   }
   float mx = pmx[0], sec = psec0;
   int idx = pidx[0];
@@ -568,6 +579,7 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
   pl.U = idivup(pl.total, pl.grid);
   pl.grid = idivup(pl.total, pl.U);
   pl.runs = idivup(pl.U, pl.n_nt) + 1;
+  { const char *e = getenv("CS_TC_DBG"); pl.dbg = e ? atoi(e) : 0; }
   const size_t slots = (size_t)pl.grid * pl.runs * TC_MT;
   const size_t rowsPad = (size_t)pl.n_mt * TC_MT;
   const unsigned int qcap = (unsigned int)(16 * rowsPad + 65536);
@@ -578,12 +590,11 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
   if ((r = ensure((void **)&bf.normA, &ws.cap[2], rowsPad * sizeof(float))) < 0) return r;
   if ((r = ensure((void **)&bf.pm, &ws.cap[3], slots * TC_PM * sizeof(float))) < 0) return r;
   if ((r = ensure((void **)&bf.rowthr, &ws.cap[4], rowsPad * 8 * sizeof(float))) < 0) return r;
-  if ((r = ensure((void **)&bf.qhead, &ws.cap[5], rowsPad * sizeof(int))) < 0) return r;
+  if ((r = ensure((void **)&bf.rcnt, &ws.cap[5], rowsPad * sizeof(unsigned))) < 0) return r;
   if ((r = ensure((void **)&bf.qv, &ws.cap[6], (size_t)qcap * sizeof(float4))) < 0) return r;
-  if ((r = ensure((void **)&bf.qexact, &ws.cap[7], (size_t)qcap * sizeof(float4))) < 0) return r;
+  if ((r = ensure((void **)&bf.rtab, &ws.cap[7], rowsPad * TC_RT * sizeof(float2))) < 0) return r;
   if ((r = ensure((void **)&bf.qgid, &ws.cap[8], (size_t)qcap * sizeof(unsigned))) < 0) return r;
   if ((r = ensure((void **)&bf.qrow, &ws.cap[9], (size_t)qcap * sizeof(int))) < 0) return r;
-  if ((r = ensure((void **)&bf.qnext, &ws.cap[10], (size_t)qcap * sizeof(int))) < 0) return r;
   if ((r = ensure((void **)&bf.fbRows, &ws.cap[11], rowsPad * sizeof(int))) < 0) return r;
   bf.qcap = qcap;
   if (!bf.bmax) {
@@ -598,14 +609,14 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
     ws.configured = true;
   }
   CS_CUDA(cudaMemsetAsync(bf.bmax, 0, 64, st));
-  CS_CUDA(cudaMemsetAsync(bf.qhead, 0xFF, (size_t)n1 * sizeof(int), st));
+  CS_CUDA(cudaMemsetAsync(bf.rcnt, 0, (size_t)n1 * sizeof(unsigned), st));
   tc_prep_kernel<<<pl.n_mt * (TC_MT / 32), 512, 0, st>>>(s1, n1, TC_M, bf.a16, bf.normA, bf.bmax, 0);
   tc_prep_kernel<<<pl.n_nt * (TC_N / 32), 512, 0, st>>>(s2, n2v, TC_N, bf.b16, nullptr, bf.bmax, 1);
   tc_gemm_kernel<1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(pl, bf);
   tc_bound_kernel<<<idivup(n1, 128), 128, 0, st>>>(pl, bf);
   tc_gemm_kernel<2><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(pl, bf);
-  tc_chain_kernel<<<sms * 2, 256, 0, st>>>(bf, s1, s2);
-  tc_final_kernel<<<idivup(n1, 128), 128, 0, st>>>(pl, bf, s1, s2);
+  tc_chain_kernel<<<sms * 8, 256, 0, st>>>(bf, s1, s2);
+  tc_final_kernel<<<idivup(n1, 64), 64, 0, st>>>(pl, bf, s1, s2);
   count_launch(7);
   CS_CUDA(cudaGetLastError());
   if ((r = match_exact_rows(s1, s2, n2, bf.fbRows, bf.counters, st)) < 0) return r;
