@@ -49,18 +49,17 @@ __device__ __forceinline__ void dog_tile(const float *__restrict__ img, int w, i
   float *s_in = s_dog;   // alias: the input tile is dead once the vertical pass is done
 
   {
-    constexpr int N = (DT_IH * DT_IW) / DT_THREADS;     // 1728 / 288 = 6 loads per thread
-    static_assert(N * DT_THREADS == DT_IH * DT_IW, "tile must divide evenly");
+    // 288 threads = 4 rows x 72 columns: thread (r0, c0) loads rows r0, r0+4, ..., r0+20 of its column.
+    // Every load is issued before the first store, so the DRAM latencies overlap.
+    constexpr int N = DT_IH / 4;
+    static_assert(DT_THREADS == 4 * DT_IW && DT_IH % 4 == 0, "load mapping");
+    const int r0 = tid / DT_IW, c0 = tid - r0 * DT_IW;
+    const float *col = img + min(max(x0 + c0 - 4, 0), w - 1);
     float v[N];
 #pragma unroll
-    for (int k = 0; k < N; k++) {       // issue every load before the first store: one DRAM round trip
-      int i = tid + DT_THREADS * k;
-      int r = i / DT_IW, c = i - r * DT_IW;
-      int gy = min(max(y0 + r - 4, 0), h - 1), gx = min(max(x0 + c - 4, 0), w - 1);
-      v[k] = __ldg(img + (size_t)gy * pitch + gx);
-    }
+    for (int k = 0; k < N; k++) v[k] = __ldg(col + (size_t)min(max(y0 + r0 + 4 * k - 4, 0), h - 1) * pitch);
 #pragma unroll
-    for (int k = 0; k < N; k++) s_in[tid + DT_THREADS * k] = v[k];
+    for (int k = 0; k < N; k++) s_in[(r0 + 4 * k) * DT_IW + c0] = v[k];
   }
   __syncthreads();
 
@@ -190,6 +189,11 @@ detect_kernel(const __grid_constant__ DetectParams P)
     // neighbour is the pixel itself, cudaSiftD.cu:1308,1331-1332) -> interior only
     if (gx > w - 2 || gy > h - 2) continue;
     const float *c = s_dog + r * DT_W + d;
+    // most pixels stay below the threshold at every scale: one test for all five
+    float cv[CS_NUM_SCALES];
+#pragma unroll
+    for (int sc = 0; sc < CS_NUM_SCALES; sc++) cv[sc] = c[(sc + 1) * (DT_H * DT_W)];
+    if (!(fmaxf(fmaxf(fmaxf(fabsf(cv[0]), fabsf(cv[1])), fmaxf(fabsf(cv[2]), fabsf(cv[3]))), fabsf(cv[4])) > thresh)) continue;
 #pragma unroll 1
     for (int sc = 0; sc < CS_NUM_SCALES; sc++) {
       const float *d1 = c + (sc + 1) * (DT_H * DT_W);

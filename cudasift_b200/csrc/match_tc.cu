@@ -333,30 +333,38 @@ tc_gemm_kernel(const TcPlan pl, const TcBuffers bf)
     const int h = (warp - 4) >> 2, q = warp & 3;
     const int rowInTile = h * TC_M + q * 32 + lane;
     const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + h * TC_N;
-    float st[8];              // PASS 1: running maxima; PASS 2: emission thresholds
+    float st[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};   // PASS 1: running maxima; PASS 2: emission thresholds
     float t2 = 0.0f;          // PASS 1: second largest group maximum of partition 0
     size_t slot = 0;
     int row = 0;
     int prevMt = -1, runIdx = 0;
     // one 32-column chunk: group j (columns 4j..4j+3) belongs to partition j
     auto process = [&](const uint32_t (&r)[32], int nt, int c) {
+      float m[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        float v0 = __uint_as_float(r[4 * j]), v1 = __uint_as_float(r[4 * j + 1]);
-        float v2 = __uint_as_float(r[4 * j + 2]), v3 = __uint_as_float(r[4 * j + 3]);
-        float m = fmaxf(fmaxf(v0, v1), fmaxf(v2, v3));
-        if (PASS == 1) {
-          if (j == 0) t2 = fmaxf(t2, fminf(st[0], m));
-          st[j] = fmaxf(st[j], m);
-        } else {
-          if (m > st[j]) {      // rare: about 3 groups per row over the whole sweep
-            unsigned int idx = atomicAdd(&bf.counters[1], 1u);
-            if (idx < bf.qcap) {
-              bf.qv[idx] = make_float4(v0, v1, v2, v3);
-              bf.qgid[idx] = (unsigned)(nt * (TC_N / 4) + c * 8 + j);
-              bf.qrow[idx] = row;
+      for (int j = 0; j < 8; j++)
+        m[j] = fmaxf(fmaxf(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1])),
+                     fmaxf(__uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3])));
+      if (PASS == 1) {
+        t2 = fmaxf(t2, fminf(st[0], m[0]));
+#pragma unroll
+        for (int j = 0; j < 8; j++) st[j] = fmaxf(st[j], m[j]);
+      } else {
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < 8; j++) any = any || (m[j] > st[j]);
+        if (any) {              // rare (about 3 groups per row over the whole sweep): one branch per chunk
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (m[j] > st[j]) {
+              unsigned int idx = atomicAdd(&bf.counters[1], 1u);
+              if (idx < bf.qcap) {
+                bf.qv[idx] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                bf.qgid[idx] = (unsigned)(nt * (TC_N / 4) + c * 8 + j);
+                bf.qrow[idx] = row;
+              }
             }
-          }
         }
       }
     };
