@@ -875,7 +875,56 @@ struct cs_extractor {
   unsigned int *h_counters;
   bool hostResults;
   int lastCount;
+  // CUDA graph of one steady-state submit (memset + 7 kernels + count D2H); only the source
+  // pointer of the first kernel changes from image to image (patched with SetParams).
+  cudaGraphExec_t gexec;
+  cudaGraph_t graph;
+  cudaGraphNode_t gnode;          // the LowPass kernel node
+  cudaKernelNodeParams gparams;
+  void *gargs[16];
+  const float *gsrc;
+  int gpitch;
+  double gblur;
+  float gthresh, glowest;
+  int submits;
 };
+
+// Capture one submit into a graph.  Returns 0 and leaves ex->gexec == NULL if anything is
+// unsupported; the caller then launches directly.
+static int extractor_capture(cs_extractor *ex, const float *d_img, int pitch, double initBlur, float thresh,
+                             float lowestScale)
+{
+  if (ex->scaleUp) return 0;
+  if (getenv("CUDASIFT_NO_GRAPH")) return 0;
+  cudaGraph_t g = nullptr;
+  if (cudaStreamBeginCapture(ex->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int r = ex->pipe.enqueue(d_img, pitch, initBlur, thresh, lowestScale, ex->d_pts, ex->maxPts, ex->stream);
+  cudaError_t e1 = cudaMemcpyAsync(ex->h_counters, ex->pipe.d_counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ex->stream);
+  cudaError_t e2 = cudaStreamEndCapture(ex->stream, &g);
+  if (r < 0 || e1 != cudaSuccess || e2 != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return 0; }
+  // find the kernel node that reads d_img (first kernel parameter == d_img)
+  size_t n = 0;
+  cudaGraphGetNodes(g, nullptr, &n);
+  std::vector<cudaGraphNode_t> nodes(n);
+  cudaGraphGetNodes(g, nodes.data(), &n);
+  bool found = false;
+  for (size_t i = 0; i < n && !found; i++) {
+    cudaGraphNodeType t;
+    if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
+    cudaKernelNodeParams kp;
+    if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess || !kp.kernelParams) continue;
+    if (*reinterpret_cast<const float *const *>(kp.kernelParams[0]) == d_img && kp.blockDim.x == 256) {
+      ex->gnode = nodes[i]; ex->gparams = kp;
+      for (int a = 0; a < 7; a++) ex->gargs[a] = kp.kernelParams[a];   // lowpass_kernel has 7 parameters
+      found = true;
+    }
+  }
+  cudaGraphExec_t ge = nullptr;
+  if (!found || cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(g); return 0; }
+  ex->graph = g; ex->gexec = ge;
+  ex->gsrc = d_img; ex->gpitch = pitch; ex->gblur = initBlur; ex->gthresh = thresh; ex->glowest = lowestScale;
+  return 0;
+}
 
 cs_extractor *cs_extractor_create(int w, int h, int numOctaves, int maxPts, int scaleUp)
 {
@@ -903,6 +952,8 @@ int cs_extractor_destroy(cs_extractor *ex)
 {
   if (!ex) return 0;
   if (ex->stream) cudaStreamSynchronize(ex->stream);
+  if (ex->gexec) cudaGraphExecDestroy(ex->gexec);
+  if (ex->graph) cudaGraphDestroy(ex->graph);
   ex->pipe.destroy();
   if (ex->d_img) cudaFree(ex->d_img);
   if (ex->d_pts) cudaFree(ex->d_pts);
@@ -917,10 +968,31 @@ int cs_extractor_destroy(cs_extractor *ex)
 int cs_extractor_submit_device(cs_extractor *ex, const float *d_img, int pitch, double initBlur, float thresh,
                                float lowestScale)
 {
+  ex->hostResults = false;
+  ex->submits++;
+  if (ex->gexec && (pitch != ex->gpitch || initBlur != ex->gblur || thresh != ex->gthresh || lowestScale != ex->glowest)) {
+    cudaGraphExecDestroy(ex->gexec); cudaGraphDestroy(ex->graph);     // parameters changed: re-capture
+    ex->gexec = nullptr; ex->graph = nullptr; ex->submits = 2;
+  }
+  if (!ex->gexec && ex->submits == 2) extractor_capture(ex, d_img, pitch, initBlur, thresh, lowestScale);
+  if (ex->gexec) {
+    if (d_img != ex->gsrc) {
+      const float *src = d_img;
+      cudaKernelNodeParams kp = ex->gparams;
+      void *args[7];
+      for (int a = 0; a < 7; a++) args[a] = ex->gargs[a];
+      args[0] = (void *)&src;
+      kp.kernelParams = args;
+      CS_CUDA(cudaGraphExecKernelNodeSetParams(ex->gexec, ex->gnode, &kp));
+      ex->gsrc = d_img;
+    }
+    CS_CUDA(cudaGraphLaunch(ex->gexec, ex->stream));
+    count_launch(cs_extract_launches_per_image(ex->numOctaves, 0));
+    return 0;
+  }
   int r = ex->pipe.enqueue(d_img, pitch, initBlur, thresh, lowestScale, ex->d_pts, ex->maxPts, ex->stream);
   if (r < 0) return r;
   CS_CUDA(cudaMemcpyAsync(ex->h_counters, ex->pipe.d_counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ex->stream));
-  ex->hostResults = false;
   return 0;
 }
 

@@ -40,7 +40,8 @@ namespace cs {
 #define TC_THREADS 384
 #define TC_RT 16            // exact scores kept per row before falling back
 #define TC_PM 12            // floats per (row, segment) of pass-1 output (8 maxima + P0 second)
-#define TC_SMEM_BYTES (TC_A_BYTES + TC_STAGES * TC_B_BYTES + 1024)
+#define TC_QS 1024          // shared-memory candidate queue entries per CTA (pass 2)
+#define TC_SMEM_BYTES (TC_A_BYTES + TC_STAGES * TC_B_BYTES + TC_QS * 24 + 1024)
 #define TC_C1 1.06e-3f      // > 2^-10 (inputs) + 2^-15 (tensor accumulate) + 2^-17 (reference chain)
 #define TC_C2 1.0e-6f       // FP16 subnormal rounding, 2^-25 * sqrt(128)
 
@@ -248,6 +249,9 @@ tc_gemm_kernel(const TcPlan pl, const TcBuffers bf)
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t *sA = smem;
   uint8_t *sB = smem + TC_A_BYTES;
+  float4 *s_qv = reinterpret_cast<float4 *>(smem + TC_A_BYTES + TC_STAGES * TC_B_BYTES);   // pass-2 candidate queue
+  uint2 *s_qm = reinterpret_cast<uint2 *>(s_qv + TC_QS);
+  __shared__ unsigned int s_qcount, s_qbase;
   __shared__ uint64_t bar_a_full, bar_a_empty, bar_b_full[TC_STAGES], bar_b_empty[TC_STAGES];
   __shared__ uint64_t bar_acc_full[2], bar_acc_empty[2];
   __shared__ uint32_t s_tmem;
@@ -257,6 +261,7 @@ tc_gemm_kernel(const TcPlan pl, const TcBuffers bf)
   const int u_begin = min(cta * pl.U, pl.total), u_end = min(u_begin + pl.U, pl.total);
 
   if (threadIdx.x == 0) {
+    s_qcount = 0;
     mbar_init(&bar_a_full, 1); mbar_init(&bar_a_empty, 1);
     for (int s = 0; s < TC_STAGES; s++) { mbar_init(&bar_b_full[s], 1); mbar_init(&bar_b_empty[s], 1); }
     for (int h = 0; h < 2; h++) { mbar_init(&bar_acc_full[h], 1); mbar_init(&bar_acc_empty[h], 128); }
@@ -357,12 +362,16 @@ tc_gemm_kernel(const TcPlan pl, const TcBuffers bf)
 #pragma unroll
           for (int j = 0; j < 8; j++)
             if (m[j] > st[j]) {
-              unsigned int idx = atomicAdd(&bf.counters[1], 1u);
-              if (idx < bf.qcap) {
-                bf.qv[idx] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                         __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                bf.qgid[idx] = (unsigned)(nt * (TC_N / 4) + c * 8 + j);
-                bf.qrow[idx] = row;
+              // shared-memory queue (a global atomic with a returned index would cost ~1 us here);
+              // flushed to the global queue once, at the end of the kernel
+              const float4 vv = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+              const unsigned int gid = (unsigned)(nt * (TC_N / 4) + c * 8 + j);
+              const unsigned int qi = atomicAdd(&s_qcount, 1u);
+              if (qi < TC_QS) { s_qv[qi] = vv; s_qm[qi] = make_uint2(gid, (unsigned)row); }
+              else {
+                const unsigned int idx = atomicAdd(&bf.counters[1], 1u);
+                if (idx < bf.qcap) { bf.qv[idx] = vv; bf.qgid[idx] = gid; bf.qrow[idx] = row; }
               }
             }
         }
@@ -420,6 +429,15 @@ tc_gemm_kernel(const TcPlan pl, const TcBuffers bf)
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+  }
+  if (PASS == 2) {      // flush the CTA's candidate queue: one global reservation, coalesced copy
+    const unsigned int nq = min(s_qcount, (unsigned)TC_QS);
+    if (threadIdx.x == 0) s_qbase = nq ? atomicAdd(&bf.counters[1], nq) : 0u;
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < nq; i += TC_THREADS) {
+      const unsigned int idx = s_qbase + i;
+      if (idx < bf.qcap) { bf.qv[idx] = s_qv[i]; bf.qgid[idx] = s_qm[i].x; bf.qrow[idx] = (int)s_qm[i].y; }
+    }
   }
 }
 

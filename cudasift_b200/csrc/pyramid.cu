@@ -45,8 +45,27 @@ lowpass_kernel(const float *__restrict__ src, int srcPitch, float *__restrict__ 
   const int x0 = blockIdx.x * LP_W, y0 = blockIdx.y * LP_H;
 
   // stage the input tile (+halo), clamped.  All loads of a thread are issued before the
-  // first shared-memory store so that their DRAM latencies overlap (one round trip, not 22).
-  {
+  // first shared-memory store so that their DRAM latencies overlap (one round trip).
+  const bool interior = (x0 >= LP_R) && (x0 + LP_W + LP_R <= w) && ((srcPitch & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (interior) {
+    // 40 rows x 34 float4 (the row segment starts at x0-4, a multiple of 4 floats)
+    constexpr int V4 = LP_IW / 4, N = (LP_IH * V4 + 255) / 256;
+    float4 v[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      int i = tid + 256 * k;
+      int r = i / V4, c = i - r * V4;
+      int gy = clampi(y0 + r - LP_R, 0, h - 1);
+      v[k] = (i < LP_IH * V4) ? __ldg(reinterpret_cast<const float4 *>(src + (size_t)gy * srcPitch + x0 - LP_R) + c)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      int i = tid + 256 * k;
+      if (i < LP_IH * V4) reinterpret_cast<float4 *>(&s_in[0][0])[i] = v[k];
+    }
+  } else {
     constexpr int N = (LP_IH * LP_IW + 255) / 256;
     float v[N];
 #pragma unroll
