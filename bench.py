@@ -355,7 +355,7 @@ def run_reference(args):
         return
     cs.InitCuda(local)                       # selects the device for this process
     dist = init_dist(world, local)
-    ref = reflib.CxxSiftLib(path)
+    ref = reflib.CxxSiftLib(path, device=local)
     B = args.batch
     c = ctypes
     images = [ref.image(imgs[i % len(imgs)]) for i in range(B)]

@@ -5,7 +5,7 @@
 // 7 DoG planes of every octave to global memory (58 MB at 1080p) and reads them back up to
 // three times; here one CTA stages an input tile in shared memory, computes the 8 blurred
 // scales and the 7 DoG planes of a 64x16 tile entirely on chip and tests the 62x14 interior
-// for extrema, so the only global traffic is one read of the octave base image and the
+// for extrema (in two phases of 4 scales), so the only global traffic is one read of the octave base image and the
 // few keypoints found.  One launch covers all octaves (the tile index selects the level).
 //
 // Per-pixel arithmetic (which products are fused, order of the sums) is pinned to the
@@ -23,9 +23,11 @@ namespace cs {
 #define DT_IW (DT_W + 8)      // 72 staged input columns
 #define DT_IH (DT_H + 8)      // 24 staged input rows
 #define DT_THREADS 288           // 9 warps: the vertical pass has 72 x 4 = 288 tasks
-#define DT_SMEM_V (CS_LAPLACE_S * DT_H * DT_IW)          // floats
-#define DT_SMEM_DOG ((CS_LAPLACE_S - 1) * DT_H * DT_W)   // floats; the input tile aliases it
-#define DT_SMEM_BYTES ((DT_SMEM_V + DT_SMEM_DOG) * 4)
+#define DT_PH 4                                          // scales blurred per phase (2 phases)
+#define DT_SMEM_V (DT_PH * DT_H * DT_IW)                 // floats: vertical results of one phase
+#define DT_SMEM_DOG ((CS_LAPLACE_S - 1) * DT_H * DT_W)   // floats: the 7 DoG planes
+#define DT_SMEM_IN (DT_IH * DT_IW)                       // floats: staged input tile
+#define DT_SMEM_BYTES ((DT_SMEM_V + DT_SMEM_DOG + DT_SMEM_IN) * 4)   // 54016 B -> 4 CTAs per SM
 
 // cudaSiftD.cu:1769-1772 / 1779-1788: sum = k0*c; sum += kj*(x[-j]+x[+j]), j=1..4.
 // SASS: FMUL(k1,p1); FFMA(k0,c); FFMA(k2,p2); FFMA(k3,p3); FFMA(k4,p4).
@@ -46,7 +48,7 @@ __device__ __forceinline__ void dog_tile(const float *__restrict__ img, int w, i
                                          float *s_v, float *s_dog)
 {
   const int tid = threadIdx.x;
-  float *s_in = s_dog;   // alias: the input tile is dead once the vertical pass is done
+  float *s_in = s_dog + DT_SMEM_DOG;
 
   {
     // 288 threads = 4 rows x 72 columns: thread (r0, c0) loads rows r0, r0+4, ..., r0+20 of its column.
@@ -63,48 +65,51 @@ __device__ __forceinline__ void dog_tile(const float *__restrict__ img, int w, i
   }
   __syncthreads();
 
-  // vertical pass: task = (column, group of 4 rows); pair sums are shared by all 8 scales
-  {
-    const int t = tid;
-    int g = t / DT_IW, c = t - g * DT_IW;
-    float in[12];
+  // Two phases of 4 scales each (halves the shared memory of the vertical results, so that 4 CTAs
+  // fit on an SM).  Vertical pass: task = (column, group of 4 rows), pair sums shared by the
+  // scales.  Horizontal pass + DoG: thread = (row, 4 consecutive columns).
+  const int vg = tid / DT_IW, vc = tid - vg * DT_IW;
+  const int hr = tid >> 4, hc0 = (tid & 15) * 4;
+  float prev[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-    for (int i = 0; i < 12; i++) in[i] = s_in[(4 * g + i) * DT_IW + c];
+  for (int ph = 0; ph < CS_LAPLACE_S / DT_PH; ph++) {
+    {
+      float in[12];
 #pragma unroll
-    for (int rr = 0; rr < 4; rr++) {
-      float cc = in[rr + 4];
-      float p1 = __fadd_rn(in[rr + 3], in[rr + 5]), p2 = __fadd_rn(in[rr + 2], in[rr + 6]);
-      float p3 = __fadd_rn(in[rr + 1], in[rr + 7]), p4 = __fadd_rn(in[rr], in[rr + 8]);
+      for (int i = 0; i < 12; i++) in[i] = s_in[(4 * vg + i) * DT_IW + vc];
 #pragma unroll
-      for (int s = 0; s < CS_LAPLACE_S; s++)
-        s_v[(s * DT_H + 4 * g + rr) * DT_IW + c] = lap_sym9(taps.k[s], cc, p1, p2, p3, p4);
+      for (int rr = 0; rr < 4; rr++) {
+        float cc = in[rr + 4];
+        float p1 = __fadd_rn(in[rr + 3], in[rr + 5]), p2 = __fadd_rn(in[rr + 2], in[rr + 6]);
+        float p3 = __fadd_rn(in[rr + 1], in[rr + 7]), p4 = __fadd_rn(in[rr], in[rr + 8]);
+#pragma unroll
+        for (int s = 0; s < DT_PH; s++)
+          s_v[(s * DT_H + 4 * vg + rr) * DT_IW + vc] = lap_sym9(taps.k[DT_PH * ph + s], cc, p1, p2, p3, p4);
+      }
     }
-  }
-  __syncthreads();
-
-  // horizontal pass + DoG: thread = (row, 4 consecutive columns), all scales (warps 0-7)
-  if (tid < 256) {
-    const int r = tid >> 4, c0 = (tid & 15) * 4;
-    float prev[4];
+    __syncthreads();
+    if (tid < 256) {
 #pragma unroll
-    for (int s = 0; s < CS_LAPLACE_S; s++) {
-      const float4 *p = reinterpret_cast<const float4 *>(&s_v[(s * DT_H + r) * DT_IW + c0]);
-      float4 a = p[0], b = p[1], c = p[2];
-      float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-      float o[4];
+      for (int s = 0; s < DT_PH; s++) {
+        const int sg = DT_PH * ph + s;
+        const float4 *p = reinterpret_cast<const float4 *>(&s_v[(s * DT_H + hr) * DT_IW + hc0]);
+        float4 a = p[0], b = p[1], c = p[2];
+        float v[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+        float o[4];
 #pragma unroll
-      for (int d = 0; d < 4; d++)
-        o[d] = lap_sym9(taps.k[s], v[d + 4], __fadd_rn(v[d + 3], v[d + 5]), __fadd_rn(v[d + 2], v[d + 6]),
-                        __fadd_rn(v[d + 1], v[d + 7]), __fadd_rn(v[d], v[d + 8]));
-      if (s > 0)
-        *reinterpret_cast<float4 *>(&s_dog[((s - 1) * DT_H + r) * DT_W + c0]) =
-            make_float4(__fsub_rn(o[0], prev[0]), __fsub_rn(o[1], prev[1]), __fsub_rn(o[2], prev[2]),
-                        __fsub_rn(o[3], prev[3]));
+        for (int d = 0; d < 4; d++)
+          o[d] = lap_sym9(taps.k[sg], v[d + 4], __fadd_rn(v[d + 3], v[d + 5]), __fadd_rn(v[d + 2], v[d + 6]),
+                          __fadd_rn(v[d + 1], v[d + 7]), __fadd_rn(v[d], v[d + 8]));
+        if (sg > 0)
+          *reinterpret_cast<float4 *>(&s_dog[((sg - 1) * DT_H + hr) * DT_W + hc0]) =
+              make_float4(__fsub_rn(o[0], prev[0]), __fsub_rn(o[1], prev[1]), __fsub_rn(o[2], prev[2]),
+                          __fsub_rn(o[3], prev[3]));
 #pragma unroll
-      for (int d = 0; d < 4; d++) prev[d] = o[d];
+        for (int d = 0; d < 4; d++) prev[d] = o[d];
+      }
     }
+    __syncthreads();
   }
-  __syncthreads();
 }
 
 // cudaSiftD.cu:1383-1429 on the shared-memory DoG tile.  d1 points at the candidate in
@@ -160,7 +165,7 @@ __device__ __noinline__ void refine_and_store(const float *d1, int gx, int gy, i
   q->subsampling = L.subsampling;
 }
 
-__global__ void __launch_bounds__(DT_THREADS)
+__global__ void __launch_bounds__(DT_THREADS, 4)
 detect_kernel(const __grid_constant__ DetectParams P)
 {
   extern __shared__ __align__(16) float smem[];

@@ -35,7 +35,7 @@ __device__ __forceinline__ float lp_sym9(const Taps9 &t, float c, float p1, floa
   return s;
 }
 
-__global__ void __launch_bounds__(256, 5)      // 510 CTAs at 1080p must fit one wave (148 x 5)
+__global__ void __launch_bounds__(256, 4)      // 510 CTAs at 1080p fit one wave (148 x 4)
 lowpass_kernel(const float *__restrict__ src, int srcPitch, float *__restrict__ dst, int dstPitch,
                int w, int h, const __grid_constant__ Taps9 taps)
 {

@@ -52,7 +52,7 @@ class quiet_stdout:
 
 
 class CxxSiftLib:
-    def __init__(self, path):
+    def __init__(self, path, device=0):
         self.path = path
         L = ctypes.CDLL(path, mode=ctypes.RTLD_LOCAL)
         self.L = L
@@ -95,7 +95,7 @@ class CxxSiftLib:
         except AttributeError:
             self._laplace = None
         with quiet_stdout():
-            self.InitCuda(0)
+            self.InitCuda(device)     # one process per GPU: the reference keeps per-process state (quirk Q12)
 
     # ---- images ----
     def image(self, arr):
