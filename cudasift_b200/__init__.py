@@ -14,7 +14,7 @@ import numpy as np
 from . import build as _build
 
 __all__ = ["SIFT_DTYPE", "lib", "InitCuda", "CudaImage", "SiftData", "InitSiftData", "FreeSiftData",
-           "AllocSiftTempMemory", "FreeSiftTempMemory", "ExtractSift", "MatchSiftData", "Extractor",
+           "AllocSiftTempMemory", "FreeSiftTempMemory", "ExtractSift", "MatchSiftData", "FindHomography", "Extractor",
            "CudaSiftError", "extract_host", "match_host"]
 
 # cudaSift.h:6-22 -- 576-byte record, descriptor at byte 64
@@ -66,6 +66,7 @@ def lib():
         "cs_match": (ip, [vp, ip, vp, ip, vp, ip, c.POINTER(c.c_double)]),
         "cs_match_host": (ip, [vp, ip, vp, ip, ip, c.POINTER(c.c_double)]),
         "cs_match_stats": (ip, [c.POINTER(c.c_ulonglong)]),
+        "cs_find_homography": (ip, [vp, ip, vp, c.POINTER(c.c_int), ip, fp, fp, fp, c.POINTER(c.c_double)]),
         "cs_lowpass": (ip, [vp, vp, ip, ip, ip, fp]),
         "cs_scaledown": (ip, [vp, vp, ip, ip, ip, ip]),
         "cs_scaleup": (ip, [vp, vp, ip, ip, ip, ip]),
@@ -234,6 +235,17 @@ def MatchSiftData(data1, data2, mode=0):
                           _ptr(data1.h_data) if data1.h_data is not None else None, int(mode), ctypes.byref(ms)),
            "MatchSiftData")
     return ms.value
+
+
+def FindHomography(data, numLoops=1000, minScore=0.85, maxAmbiguity=0.95, thresh=5.0, seed=None):
+    """matching.cu:1000-1087; returns (3x3 homography, numMatches, ms).  seed: srand() value."""
+    H = np.zeros(9, np.float32)
+    n, ms = ctypes.c_int(0), ctypes.c_double(0.0)
+    if seed is not None:
+        ctypes.CDLL(None).srand(int(seed))
+    _check(lib().cs_find_homography(data.d_data, data.numPts, _ptr(H), ctypes.byref(n), int(numLoops), float(minScore),
+                                    float(maxAmbiguity), float(thresh), ctypes.byref(ms)), "FindHomography")
+    return H.reshape(3, 3), n.value, ms.value
 
 
 def match_stats():

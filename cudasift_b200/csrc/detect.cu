@@ -182,7 +182,7 @@ __device__ __forceinline__ void tile_coords(const DetectParams &P, int tile, int
   x0 = bx * (DT_W - 2); y0 = by * (DT_H - 2);
 }
 
-// Persistent CTAs (4 per SM) stride over the tiles of all octaves.  The input tile of the NEXT
+// Persistent CTAs (4 per SM) pull the tiles of all octaves from a dynamic scheduler.  The input tile of the NEXT
 // iteration is loaded into registers before the current one is processed, so the DRAM latency of
 // the only global read of this kernel is hidden behind a whole tile of arithmetic.
 __global__ void __launch_bounds__(DT_THREADS, 4)
@@ -201,13 +201,17 @@ detect_kernel(const __grid_constant__ DetectParams P)
   float pre[DT_LD];
   tile_load(P.lev[level].img, P.lev[level].w, P.lev[level].h, P.lev[level].pitch, x0, y0, pre);
 
+  __shared__ int s_next;
   while (true) {
     const DetectLevel &L = P.lev[level];
     const int w = L.w, h = L.h, cx0 = x0, cy0 = y0;
     tile_store(s_in, pre);
+    // dynamic tile scheduler: tiles beyond the first wave are handed out by an atomic counter
+    // (reset with the other per-image counters), which evens out the tail
+    if (threadIdx.x == 0) s_next = (int)gridDim.x + (int)atomicAdd(&P.counters[2], 1u);
     __syncthreads();
     // prefetch the next tile of this CTA
-    const int next = tile + gridDim.x;
+    const int next = s_next;
     int nlevel = level;
     if (next < P.totalTiles) {
       tile_coords(P, next, nlevel, x0, y0);

@@ -77,6 +77,11 @@ int cs_match_host(void *h_s1, int n1, const void *h_s2, int n2, int mode, double
  * pairs that took the exact-scan fallback, out[3]=path used (1 or 2). */
 int cs_match_stats(unsigned long long out[4]);
 
+/* FindHomography (matching.cu:1000-1087): RANSAC over the matches of set 1.  homography: 9 floats
+ * (row-major 3x3, [8] = 1).  Samples are drawn with rand(): srand() beforehand for repeatability. */
+int cs_find_homography(void *d_pts, int numPts, float *homography, int *numMatches, int numLoops,
+                       float minScore, float maxAmbiguity, float thresh, double *ms);
+
 /* ---- stage-level entry points (reference: cudaSiftH.h:11-22), used by parity tests ---- */
 int cs_lowpass(const float *d_src, float *d_dst, int width, int height, int pitch, float sigma);
 int cs_scaledown(const float *d_src, float *d_dst, int width, int height, int pitch, int newpitch);

@@ -58,6 +58,8 @@ def lib():
         L.oracle_extract.restype = ip
         L.oracle_match.argtypes = [vp, ip, vp, ip]
         L.oracle_match_mt.argtypes = [vp, ip, vp, ip, ip]
+        L.oracle_find_homography.argtypes = [vp, ip, vp, vp, ip, fp, fp, fp]
+        L.oracle_find_homography.restype = c.c_double
         _lib = L
     return _lib
 
@@ -131,3 +133,14 @@ def match(s1, s2, threads=1):
     else:
         lib().oracle_match(_p(s1), len(s1), _p(s2), len(s2))
     return s1
+
+
+def find_homography(pts, numLoops=1000, minScore=0.85, maxAmbiguity=0.95, thresh=5.0, seed=None):
+    """Returns (3x3 homography, numMatches).  seed: srand() value set just before the call."""
+    pts = np.ascontiguousarray(pts, SIFT_DTYPE)
+    H = np.zeros(9, np.float32)
+    n = ctypes.c_int(0)
+    if seed is not None:
+        ctypes.CDLL(None).srand(int(seed))
+    lib().oracle_find_homography(_p(pts), len(pts), _p(H), ctypes.byref(n), numLoops, minScore, maxAmbiguity, thresh)
+    return H.reshape(3, 3), n.value

@@ -607,3 +607,125 @@ void oracle_match_mt(OracleSiftPoint *s1, int n1, const OracleSiftPoint *s2, int
   }
   for (int t = 0; t < used; t++) pthread_join(th[t], NULL);
 }
+
+/* ------------------------------------------------------------------ RANSAC homography */
+
+static float mul_rz(float a, float b)
+{ /* __fmul_rz: the double product is exact, then round toward zero */
+  double p = (double)a * (double)b;
+  float f = (float)p;
+  if (fabs((double)f) > fabs(p)) f = nextafterf(f, 0.0f);
+  return f;
+}
+
+static void invert8(float a[8][8], float inv[8][8])
+{ /* matching.cu:821-905 (LU decomposition with implicit pivoting, then 8 back substitutions) */
+  int indx[8], imax = 0;
+  float vv[8];
+  for (int i = 0; i < 8; i++) {
+    float big = 0.0f;
+    for (int j = 0; j < 8; j++) { float t = fabsf(a[i][j]); if (t > big) big = t; }
+    vv[i] = big > 0.0f ? (float)(1.0 / (double)big) : 1e16f;
+  }
+  for (int j = 0; j < 8; j++) {
+    for (int i = 0; i < j; i++) {
+      float sum = a[i][j];
+      for (int k = 0; k < i; k++) sum = fmaf(-a[i][k], a[k][j], sum);
+      a[i][j] = sum;
+    }
+    float big = 0.0f;
+    for (int i = j; i < 8; i++) {
+      float sum = a[i][j];
+      for (int k = 0; k < j; k++) sum = fmaf(-a[i][k], a[k][j], sum);
+      a[i][j] = sum;
+      float dum = vv[i] * fabsf(sum);
+      if (dum >= big) { big = dum; imax = i; }
+    }
+    if (j != imax) {
+      for (int k = 0; k < 8; k++) { float t = a[imax][k]; a[imax][k] = a[j][k]; a[j][k] = t; }
+      vv[imax] = vv[j];
+    }
+    indx[j] = imax;
+    if (a[j][j] == 0.0f) a[j][j] = 1e-16f;
+    if (j != 7) {
+      float dum = (float)(1.0 / (double)a[j][j]);
+      for (int i = j + 1; i < 8; i++) a[i][j] *= dum;
+    }
+  }
+  for (int j = 0; j < 8; j++) {
+    float b[8];
+    for (int k = 0; k < 8; k++) b[k] = 0.0f;
+    b[j] = 1.0f;
+    int ii = -1;
+    for (int i = 0; i < 8; i++) {
+      int ip = indx[i];
+      float sum = b[ip];
+      b[ip] = b[i];
+      if (ii != -1) { for (int k = ii; k < i; k++) sum = fmaf(-a[i][k], b[k], sum); }
+      else if (sum != 0.0f) ii = i;
+      b[i] = sum;
+    }
+    for (int i = 7; i >= 0; i--) {
+      float sum = b[i];
+      for (int k = i + 1; k < 8; k++) sum = fmaf(-a[i][k], b[k], sum);
+      b[i] = sum / a[i][i];
+    }
+    for (int i = 0; i < 8; i++) inv[i][j] = b[i];
+  }
+}
+
+double oracle_find_homography(const OracleSiftPoint *pts, int numPts, float *homography, int *numMatches,
+                              int numLoops, float minScore, float maxAmbiguity, float thresh)
+{ /* matching.cu:1000-1087; samples are drawn with rand() in the reference's order */
+  *numMatches = 0;
+  for (int i = 0; i < 9; i++) homography[i] = (i % 4 == 0) ? 1.0f : 0.0f;
+  numLoops = (numLoops + 15) / 16 * 16;
+  if (numPts < 8) return 0.0;
+  int *valid = (int *)malloc(sizeof(int) * numPts), numValid = 0;
+  for (int i = 0; i < numPts; i++)
+    if (pts[i].score > minScore && pts[i].ambiguity < maxAmbiguity) valid[numValid++] = i;
+  if (numValid >= 8) {
+    int *rp = (int *)malloc(sizeof(int) * 4 * (size_t)numLoops);
+    for (int i = 0; i < numLoops; i++) {
+      int p1 = rand() % numValid, p2 = rand() % numValid, p3 = rand() % numValid, p4 = rand() % numValid;
+      while (p2 == p1) p2 = rand() % numValid;
+      while (p3 == p1 || p3 == p2) p3 = rand() % numValid;
+      while (p4 == p1 || p4 == p2 || p4 == p3) p4 = rand() % numValid;
+      rp[4 * i] = valid[p1]; rp[4 * i + 1] = valid[p2]; rp[4 * i + 2] = valid[p3]; rp[4 * i + 3] = valid[p4];
+    }
+    int maxCount = -1;
+    float thresh2 = thresh * thresh;
+    for (int l = 0; l < numLoops; l++) {
+      float a[8][8], ia[8][8], b[8], hm[8];
+      for (int i = 0; i < 4; i++) {                              /* matching.cu:916-938 */
+        const OracleSiftPoint *p = pts + rp[4 * l + i];
+        float x1 = p->xpos, y1 = p->ypos, x2 = p->match_xpos, y2 = p->match_ypos;
+        float *r1 = a[2 * i], *r2 = a[2 * i + 1];
+        r1[0] = x1; r1[1] = y1; r1[2] = 1.0f; r1[3] = r1[4] = r1[5] = 0.0f; r1[6] = -x2 * x1; r1[7] = -x2 * y1;
+        r2[0] = r2[1] = r2[2] = 0.0f; r2[3] = x1; r2[4] = y1; r2[5] = 1.0f; r2[6] = -y2 * x1; r2[7] = -y2 * y1;
+        b[2 * i] = x2; b[2 * i + 1] = y2;
+      }
+      invert8(a, ia);
+      for (int j = 0; j < 8; j++) {
+        float sum = 0.0f;
+        for (int i = 0; i < 8; i++) sum = fmaf(ia[j][i], b[i], sum);
+        hm[j] = sum;
+      }
+      int cnt = 0;                                               /* matching.cu:969-982 */
+      for (int i = 0; i < numPts; i++) {
+        float x1 = pts[i].xpos, y1 = pts[i].ypos, x2 = pts[i].match_xpos, y2 = pts[i].match_ypos;
+        float nomx = (mul_rz(hm[0], x1) + mul_rz(hm[1], y1)) + hm[2];
+        float nomy = (mul_rz(hm[3], x1) + mul_rz(hm[4], y1)) + hm[5];
+        float deno = (mul_rz(hm[6], x1) + mul_rz(hm[7], y1)) + 1.0f;
+        float errx = mul_rz(x2, deno) - nomx, erry = mul_rz(y2, deno) - nomy;
+        float err2 = mul_rz(errx, errx) + mul_rz(erry, erry);
+        if (err2 < mul_rz(thresh2, mul_rz(deno, deno))) cnt++;
+      }
+      if (cnt > maxCount) { maxCount = cnt; for (int j = 0; j < 8; j++) homography[j] = hm[j]; }
+    }
+    *numMatches = maxCount;
+    free(rp);
+  }
+  free(valid);
+  return 0.0;
+}

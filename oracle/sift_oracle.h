@@ -85,6 +85,11 @@ void oracle_match(OracleSiftPoint *s1, int n1, const OracleSiftPoint *s2, int n2
 void oracle_match_mt(OracleSiftPoint *s1, int n1, const OracleSiftPoint *s2, int n2,
                      int nthreads);
 
+/* matching.cu:1000-1087 (FindHomography, RANSAC with rand()).  Tests all numPts points (the
+ * reference also visits up to 15 uninitialised padding entries). */
+double oracle_find_homography(const OracleSiftPoint *pts, int numPts, float *homography, int *numMatches,
+                              int numLoops, float minScore, float maxAmbiguity, float thresh);
+
 #ifdef __cplusplus
 }
 #endif
