@@ -41,34 +41,33 @@ __device__ __forceinline__ float lap_sym9(const float *k, float c, float p1, flo
   return s;
 }
 
-// Stage a 72x24 input tile: 288 threads = 4 rows x 72 columns, thread (r0, c0) holds rows
-// r0, r0+4, ..., r0+20 of its column.  The loads go to registers first (tile_load) so that they
-// can be issued one whole tile ahead of their use (software prefetch, see detect_kernel).
-#define DT_LD (DT_IH / 4)
-__device__ __forceinline__ void tile_load(const float *__restrict__ img, int w, int h, int pitch, int x0, int y0,
-                                          float (&v)[DT_LD])
-{
-  static_assert(DT_THREADS == 4 * DT_IW && DT_IH % 4 == 0, "load mapping");
-  const int tid = threadIdx.x;
-  const int r0 = tid / DT_IW, c0 = tid - r0 * DT_IW;
-  const float *col = img + min(max(x0 + c0 - 4, 0), w - 1);
-#pragma unroll
-  for (int k = 0; k < DT_LD; k++) v[k] = __ldg(col + (size_t)min(max(y0 + r0 + 4 * k - 4, 0), h - 1) * pitch);
-}
-__device__ __forceinline__ void tile_store(float *s_in, const float (&v)[DT_LD])
-{
-  const int tid = threadIdx.x;
-  const int r0 = tid / DT_IW, c0 = tid - r0 * DT_IW;
-#pragma unroll
-  for (int k = 0; k < DT_LD; k++) s_in[(r0 + 4 * k) * DT_IW + c0] = v[k];
-}
-
-// Blur the staged tile (already in s_in, barrier passed) at 8 scales and leave the 7 DoG planes
-// in s_dog[7][DT_H][DT_W].
-__device__ __forceinline__ void dog_tile(const LaplaceTaps &taps, float *s_v, float *s_dog)
+// Blur the staged tile at 8 scales and leave the 7 DoG planes in s_dog[7][DT_H][DT_W].
+// (x0,y0) = image coordinates of DoG element (0,0).
+// If s_list != nullptr, every interior pixel whose |DoG| exceeds `thresh` in one of the five
+// testable planes is appended to s_list (r*64+d), decided on the register copies of the DoG
+// values -- the extrema test then only visits those pixels.
+__device__ __forceinline__ void dog_tile(const float *__restrict__ img, int w, int h, int pitch,
+                                         int x0, int y0, const LaplaceTaps &taps,
+                                         float *s_v, float *s_dog,
+                                         float thresh = 0.0f, unsigned short *s_list = nullptr, int *s_cnt = nullptr)
 {
   const int tid = threadIdx.x;
   float *s_in = s_dog + DT_SMEM_DOG;
+
+  {
+    // 288 threads = 4 rows x 72 columns: thread (r0, c0) loads rows r0, r0+4, ..., r0+20 of its column.
+    // Every load is issued before the first store, so the DRAM latencies overlap.
+    constexpr int N = DT_IH / 4;
+    static_assert(DT_THREADS == 4 * DT_IW && DT_IH % 4 == 0, "load mapping");
+    const int r0 = tid / DT_IW, c0 = tid - r0 * DT_IW;
+    const float *col = img + min(max(x0 + c0 - 4, 0), w - 1);
+    float v[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) v[k] = __ldg(col + (size_t)min(max(y0 + r0 + 4 * k - 4, 0), h - 1) * pitch);
+#pragma unroll
+    for (int k = 0; k < N; k++) s_in[(r0 + 4 * k) * DT_IW + c0] = v[k];
+  }
+  __syncthreads();
 
   // Two phases of 4 scales each (halves the shared memory of the vertical results, so that 4 CTAs
   // fit on an SM).  Vertical pass: task = (column, group of 4 rows), pair sums shared by the
@@ -76,6 +75,7 @@ __device__ __forceinline__ void dog_tile(const LaplaceTaps &taps, float *s_v, fl
   const int vg = tid / DT_IW, vc = tid - vg * DT_IW;
   const int hr = tid >> 4, hc0 = (tid & 15) * 4;
   float prev[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  float amax[4] = {0.0f, 0.0f, 0.0f, 0.0f};     // max |DoG| over planes 1..5 of this thread's 4 pixels
 #pragma unroll
   for (int ph = 0; ph < CS_LAPLACE_S / DT_PH; ph++) {
     {
@@ -105,12 +105,27 @@ __device__ __forceinline__ void dog_tile(const LaplaceTaps &taps, float *s_v, fl
         for (int d = 0; d < 4; d++)
           o[d] = lap_sym9(taps.k[sg], v[d + 4], __fadd_rn(v[d + 3], v[d + 5]), __fadd_rn(v[d + 2], v[d + 6]),
                           __fadd_rn(v[d + 1], v[d + 7]), __fadd_rn(v[d], v[d + 8]));
-        if (sg > 0)
-          *reinterpret_cast<float4 *>(&s_dog[((sg - 1) * DT_H + hr) * DT_W + hc0]) =
-              make_float4(__fsub_rn(o[0], prev[0]), __fsub_rn(o[1], prev[1]), __fsub_rn(o[2], prev[2]),
-                          __fsub_rn(o[3], prev[3]));
+        if (sg > 0) {
+          const float4 dg = make_float4(__fsub_rn(o[0], prev[0]), __fsub_rn(o[1], prev[1]), __fsub_rn(o[2], prev[2]),
+                                        __fsub_rn(o[3], prev[3]));
+          *reinterpret_cast<float4 *>(&s_dog[((sg - 1) * DT_H + hr) * DT_W + hc0]) = dg;
+          if (sg >= 2 && sg <= 6) {             // DoG planes 1..5 are the ones tested for extrema
+            amax[0] = fmaxf(amax[0], fabsf(dg.x)); amax[1] = fmaxf(amax[1], fabsf(dg.y));
+            amax[2] = fmaxf(amax[2], fabsf(dg.z)); amax[3] = fmaxf(amax[3], fabsf(dg.w));
+          }
+        }
 #pragma unroll
         for (int d = 0; d < 4; d++) prev[d] = o[d];
+      }
+    }
+    if (ph == CS_LAPLACE_S / DT_PH - 1 && s_list != nullptr && tid < 256 && hr >= 1 && hr <= DT_H - 2) {
+      // image-border pixels can never be strict extrema in the reference (their clamped
+      // neighbour is the pixel itself, cudaSiftD.cu:1308,1331-1332) -> interior only
+#pragma unroll
+      for (int d = 0; d < 4; d++) {
+        const int dd = hc0 + d;
+        if (amax[d] > thresh && dd >= 1 && dd <= DT_W - 2 && x0 + dd <= w - 2 && y0 + hr <= h - 2)
+          s_list[atomicAdd(s_cnt, 1)] = (unsigned short)(hr * DT_W + dd);
       }
     }
     __syncthreads();
@@ -170,107 +185,64 @@ __device__ __noinline__ void refine_and_store(const float *d1, int gx, int gy, i
   q->subsampling = L.subsampling;
 }
 
-// tile index -> (level, origin)
-__device__ __forceinline__ void tile_coords(const DetectParams &P, int tile, int &level, int &x0, int &y0)
-{
-  level = 0;
-#pragma unroll 1
-  for (int l = 1; l < P.numLevels; l++)
-    if (tile >= P.lev[l].tileBase) level = l;
-  const int t = tile - P.lev[level].tileBase;
-  const int by = t / P.lev[level].tilesX, bx = t - by * P.lev[level].tilesX;
-  x0 = bx * (DT_W - 2); y0 = by * (DT_H - 2);
-}
-
-// Persistent CTAs (4 per SM) pull the tiles of all octaves from a dynamic scheduler.  The input tile of the NEXT
-// iteration is loaded into registers before the current one is processed, so the DRAM latency of
-// the only global read of this kernel is hidden behind a whole tile of arithmetic.
 __global__ void __launch_bounds__(DT_THREADS, 4)
 detect_kernel(const __grid_constant__ DetectParams P)
 {
   extern __shared__ __align__(16) float smem[];
   float *s_v = smem;
   float *s_dog = smem + DT_SMEM_V;
-  float *s_in = s_dog + DT_SMEM_DOG;
-  const float thresh = P.thresh;
 
-  int tile = blockIdx.x;
-  if (tile >= P.totalTiles) return;
-  int level, x0, y0;
-  tile_coords(P, tile, level, x0, y0);
-  float pre[DT_LD];
-  tile_load(P.lev[level].img, P.lev[level].w, P.lev[level].h, P.lev[level].pitch, x0, y0, pre);
-
-  __shared__ int s_next;
-  while (true) {
-    const DetectLevel &L = P.lev[level];
-    const int w = L.w, h = L.h, cx0 = x0, cy0 = y0;
-    tile_store(s_in, pre);
-    // dynamic tile scheduler: tiles beyond the first wave are handed out by an atomic counter
-    // (reset with the other per-image counters), which evens out the tail
-    if (threadIdx.x == 0) s_next = (int)gridDim.x + (int)atomicAdd(&P.counters[2], 1u);
-    __syncthreads();
-    // prefetch the next tile of this CTA
-    const int next = s_next;
-    int nlevel = level;
-    if (next < P.totalTiles) {
-      tile_coords(P, next, nlevel, x0, y0);
-      tile_load(P.lev[nlevel].img, P.lev[nlevel].w, P.lev[nlevel].h, P.lev[nlevel].pitch, x0, y0, pre);
-    }
-
-    dog_tile(L.taps, s_v, s_dog);
-
-    // 3x3x3 extrema on the 62x14 interior: 3 pixels per thread; the five centre values of a
-    // pixel are loaded together and one threshold test covers its five scales
-    constexpr int NPX = ((DT_H - 2) * (DT_W - 2) + DT_THREADS - 1) / DT_THREADS;
-#pragma unroll
-    for (int k = 0; k < NPX; k++) {
-      const int i = threadIdx.x + k * DT_THREADS;
-      if (i >= (DT_H - 2) * (DT_W - 2)) continue;
-      float cv[CS_NUM_SCALES];
-      {
-        const int r = i / (DT_W - 2) + 1, d = i - (r - 1) * (DT_W - 2) + 1;
-#pragma unroll
-        for (int sc = 0; sc < CS_NUM_SCALES; sc++) cv[sc] = s_dog[(sc + 1) * (DT_H * DT_W) + r * DT_W + d];
-      }
-      const float mx = fmaxf(fmaxf(fmaxf(fabsf(cv[0]), fabsf(cv[1])), fmaxf(fabsf(cv[2]), fabsf(cv[3]))), fabsf(cv[4]));
-      if (!(mx > thresh)) continue;
-      const int r = i / (DT_W - 2) + 1, d = i - (r - 1) * (DT_W - 2) + 1;
-      const int gx = cx0 + d, gy = cy0 + r;
-      // image-border pixels can never be strict extrema in the reference (their clamped
-      // neighbour is the pixel itself, cudaSiftD.cu:1308,1331-1332) -> interior only
-      if (gx > w - 2 || gy > h - 2) continue;
-      const float *c = s_dog + r * DT_W + d;
+  // which level does this tile belong to?  (levels are listed coarsest-last)
+  int level = 0;
 #pragma unroll 1
-      for (int sc = 0; sc < CS_NUM_SCALES; sc++) {
-        const float *d1 = c + (sc + 1) * (DT_H * DT_W);
-        const float v = d1[0];
-        if (!(fabsf(v) > thresh)) continue;
-        bool ext = true;
-        if (v > 0.0f) {
+  for (int l = 1; l < P.numLevels; l++)
+    if ((int)blockIdx.x >= P.lev[l].tileBase) level = l;
+  const DetectLevel &L = P.lev[level];
+  const int tile = blockIdx.x - L.tileBase;
+  const int by = tile / L.tilesX, bx = tile - by * L.tilesX;
+  const int x0 = bx * (DT_W - 2), y0 = by * (DT_H - 2);
+  const int w = L.w, h = L.h;
+
+  __shared__ unsigned short s_list[(DT_H - 2) * (DT_W - 2)];
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  const float thresh = P.thresh;
+  dog_tile(L.img, w, h, L.pitch, x0, y0, L.taps, s_v, s_dog, thresh, s_list, &s_cnt);
+
+  // 3x3x3 extrema, only on the pixels the blur pass flagged (|DoG| > thresh at some scale)
+  const int ncand = s_cnt;
+  for (int i = threadIdx.x; i < ncand; i += DT_THREADS) {
+    const int rd = s_list[i];
+    const int r = rd / DT_W, d = rd - r * DT_W;
+    const int gx = x0 + d, gy = y0 + r;
+    const float *c = s_dog + rd;
+#pragma unroll 1
+    for (int sc = 0; sc < CS_NUM_SCALES; sc++) {
+      const float *d1 = c + (sc + 1) * (DT_H * DT_W);
+      float v = d1[0];
+      if (!(fabsf(v) > thresh)) continue;
+      bool ext = true;
+      if (v > 0.0f) {
 #pragma unroll
-          for (int pl = -1; pl <= 1; pl++)
+        for (int pl = -1; pl <= 1; pl++)
 #pragma unroll
-            for (int dy = -1; dy <= 1; dy++)
+          for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
-              for (int dx = -1; dx <= 1; dx++)
-                if (pl != 0 || dy != 0 || dx != 0)
-                  ext = ext && (v > d1[pl * (DT_H * DT_W) + dy * DT_W + dx]);
-        } else {
+            for (int dx = -1; dx <= 1; dx++)
+              if (pl != 0 || dy != 0 || dx != 0)
+                ext = ext && (v > d1[pl * (DT_H * DT_W) + dy * DT_W + dx]);
+      } else {
 #pragma unroll
-          for (int pl = -1; pl <= 1; pl++)
+        for (int pl = -1; pl <= 1; pl++)
 #pragma unroll
-            for (int dy = -1; dy <= 1; dy++)
+          for (int dy = -1; dy <= 1; dy++)
 #pragma unroll
-              for (int dx = -1; dx <= 1; dx++)
-                if (pl != 0 || dy != 0 || dx != 0)
-                  ext = ext && (v < d1[pl * (DT_H * DT_W) + dy * DT_W + dx]);
-        }
-        if (ext) refine_and_store(d1, gx, gy, sc, L, P);
+            for (int dx = -1; dx <= 1; dx++)
+              if (pl != 0 || dy != 0 || dx != 0)
+                ext = ext && (v < d1[pl * (DT_H * DT_W) + dy * DT_W + dx]);
       }
+      if (ext) refine_and_store(d1, gx, gy, sc, L, P);
     }
-    if (next >= P.totalTiles) break;
-    tile = next; level = nlevel;
   }
 }
 
@@ -282,14 +254,7 @@ int launch_detect(const DetectParams &p, cudaStream_t st)
     configured = true;
   }
   if (p.totalTiles <= 0) return 0;
-  static int maxGrid = 0;
-  if (!maxGrid) {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    maxGrid = 4 * sms;                               // 4 resident CTAs per SM
-  }
-  detect_kernel<<<p.totalTiles < maxGrid ? p.totalTiles : maxGrid, DT_THREADS, DT_SMEM_BYTES, st>>>(p);
+  detect_kernel<<<p.totalTiles, DT_THREADS, DT_SMEM_BYTES, st>>>(p);
   count_launch();
   CS_CUDA(cudaGetLastError());
   return 0;
@@ -306,11 +271,7 @@ dog_planes_kernel(const float *__restrict__ img, float *__restrict__ dog, int w,
   float *s_dog = smem + DT_SMEM_V;
   const int by = blockIdx.x / tilesX, bx = blockIdx.x - by * tilesX;
   const int x0 = bx * (DT_W - 2), y0 = by * (DT_H - 2);
-  float pre[DT_LD];
-  tile_load(img, w, h, pitch, x0, y0, pre);
-  tile_store(s_dog + DT_SMEM_DOG, pre);
-  __syncthreads();
-  dog_tile(taps, s_v, s_dog);
+  dog_tile(img, w, h, pitch, x0, y0, taps, s_v, s_dog);
   const size_t plane = (size_t)h * pitch;
   for (int i = threadIdx.x; i < (CS_LAPLACE_S - 1) * DT_H * DT_W; i += DT_THREADS) {
     int s = i / (DT_H * DT_W), rem = i - s * (DT_H * DT_W);

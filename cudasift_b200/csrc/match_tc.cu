@@ -144,14 +144,20 @@ struct TcBuffers {
 
 // ------------------------------------------------------------------------------ prep
 // block = 32 rows x 16 chunks; writes chunk-major tiles: blob(tile)[chunk][row][8 halves]
+// One launch converts both sets: CTAs [0, blocksA) take set 1, the rest set 2.
 __global__ void __launch_bounds__(512)
-tc_prep_kernel(const SiftPoint *__restrict__ pts, int nvalid, int rowsPerTile, __half *__restrict__ out,
-               float *__restrict__ norms, float *__restrict__ bmax, int isB)
+tc_prep_kernel(const SiftPoint *__restrict__ ptsA, int nA, __half *__restrict__ outA, float *__restrict__ norms,
+               int blocksA, const SiftPoint *__restrict__ ptsB, int nB, __half *__restrict__ outB,
+               float *__restrict__ bmax)
 {
   __shared__ float s_sq[16][33];
   __shared__ int s_bad;
+  const int isB = (int)blockIdx.x >= blocksA;
+  const SiftPoint *__restrict__ pts = isB ? ptsB : ptsA;
+  const int nvalid = isB ? nB : nA, rowsPerTile = isB ? TC_N : TC_M;
+  __half *__restrict__ out = isB ? outB : outA;
   const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
-  const int row = blockIdx.x * 32 + lane;
+  const int row = (isB ? (int)blockIdx.x - blocksA : (int)blockIdx.x) * 32 + lane;
   if (threadIdx.x == 0) s_bad = 0;
   __syncthreads();
   float v[8];
@@ -636,14 +642,14 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
   }
   CS_CUDA(cudaMemsetAsync(bf.bmax, 0, 64, st));
   CS_CUDA(cudaMemsetAsync(bf.rcnt, 0, (size_t)n1 * sizeof(unsigned), st));
-  tc_prep_kernel<<<pl.n_mt * (TC_MT / 32), 512, 0, st>>>(s1, n1, TC_M, bf.a16, bf.normA, bf.bmax, 0);
-  tc_prep_kernel<<<pl.n_nt * (TC_N / 32), 512, 0, st>>>(s2, n2v, TC_N, bf.b16, nullptr, bf.bmax, 1);
+  const int blocksA = pl.n_mt * (TC_MT / 32), blocksB = pl.n_nt * (TC_N / 32);
+  tc_prep_kernel<<<blocksA + blocksB, 512, 0, st>>>(s1, n1, bf.a16, bf.normA, blocksA, s2, n2v, bf.b16, bf.bmax);
   tc_gemm_kernel<1><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(pl, bf);
   tc_bound_kernel<<<idivup(n1, 128), 128, 0, st>>>(pl, bf);
   tc_gemm_kernel<2><<<pl.grid, TC_THREADS, TC_SMEM_BYTES, st>>>(pl, bf);
   tc_chain_kernel<<<sms * 8, 256, 0, st>>>(bf, s1, s2);
   tc_final_kernel<<<idivup(n1, 64), 64, 0, st>>>(pl, bf, s1, s2);
-  count_launch(7);
+  count_launch(6);
   CS_CUDA(cudaGetLastError());
   if ((r = match_exact_rows(s1, s2, n2, bf.fbRows, bf.counters, st)) < 0) return r;
   // inputs FP16 cannot bound (|x| >= 32768, NaN, Inf) or a queue overflow: redo everything exactly
