@@ -231,10 +231,39 @@ def run_product(args):
     e2e_s = reduce_max(dist, time.perf_counter() - t0)
     e2e_value = e2e_images * world / e2e_s
 
+    # --- extension: 8-bit uploads (4x less PCIe traffic, exact conversion on the device) ---
+    h8 = []
+    for i in range(min(B, 8)):
+        p = L.cs_host_alloc_pinned(W * H)
+        a8 = np.clip(np.rint(imgs[i % len(imgs)]), 0, 255).astype(np.uint8)
+        ctypes.memmove(p, a8.ctypes.data, W * H)
+        h8.append(p)
+
+    def run_e2e_u8(n):
+        busy = [False] * S
+        for i in range(n):
+            s = i % S
+            if busy[s]:
+                exs[s].wait()
+            exs[s].submit_host_u8(h8[i % len(h8)], INIT_BLUR, THRESH, 0.0)
+            busy[s] = True
+        for s in range(S):
+            if busy[s]:
+                exs[s].wait()
+    run_e2e_u8(2 * S)
+    barrier_and_sync(dist)
+    t0 = time.perf_counter()
+    run_e2e_u8(e2e_images)
+    barrier_and_sync(dist)
+    e2e_u8_value = e2e_images * world / reduce_max(dist, time.perf_counter() - t0)
+
     # --- synchronous classic call, one image at a time (reference-shaped usage) ---
     hp = np.zeros(MAX_PTS, cs.SIFT_DTYPE)
     t0 = time.perf_counter()
     nsync = 16
+    for i in range(2):       # warm the internal pipeline of the synchronous path
+        L.cs_extract_host(himgs[i % len(himgs)], W, H, OCTAVES, INIT_BLUR, THRESH, 0.0, 0, hp.ctypes.data, MAX_PTS)
+    t0 = time.perf_counter()
     for i in range(nsync):
         L.cs_extract_host(himgs[i % len(himgs)], W, H, OCTAVES, INIT_BLUR, THRESH, 0.0, 0, hp.ctypes.data, MAX_PTS)
     sync_ms = (time.perf_counter() - t0) / nsync * 1e3
@@ -252,7 +281,8 @@ def run_product(args):
         "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": B * W * H * 4,
                 "d2h_bytes_per_step": int(d2h_bytes / e2e_images * B), "images": e2e_images * world,
                 "api": "cs_extractor_submit_host/cs_extractor_wait (pinned host buffers, %d in flight)" % S,
-                "sync_call_ms": round(sync_ms, 3)},
+                "sync_call_ms": round(sync_ms, 3),
+                "u8_upload_images_per_s": round(e2e_u8_value, 1)},
         "gpu_launches": int(launches * world),
         "wall_s": round(wall, 4),
     }

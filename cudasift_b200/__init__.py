@@ -77,6 +77,7 @@ def lib():
         "cs_extractor_destroy": (ip, [vp]),
         "cs_extractor_submit_device": (ip, [vp, vp, ip, c.c_double, fp, fp]),
         "cs_extractor_submit_host": (ip, [vp, vp, c.c_double, fp, fp]),
+        "cs_extractor_submit_host_u8": (ip, [vp, vp, c.c_double, fp, fp]),
         "cs_extractor_wait": (ip, [vp]),
         "cs_event_create": (vp, []),
         "cs_event_destroy": (ip, [vp]),
@@ -290,6 +291,9 @@ class Extractor:
 
     def submit_host(self, h_img_ptr, initBlur=1.0, thresh=3.0, lowestScale=0.0):
         _check(lib().cs_extractor_submit_host(self.handle, h_img_ptr, initBlur, thresh, lowestScale), "submit")
+
+    def submit_host_u8(self, h_img_ptr, initBlur=1.0, thresh=3.0, lowestScale=0.0):
+        _check(lib().cs_extractor_submit_host_u8(self.handle, h_img_ptr, initBlur, thresh, lowestScale), "submit")
 
     def wait(self):
         return _check(lib().cs_extractor_wait(self.handle), "wait")

@@ -871,6 +871,7 @@ struct cs_extractor {
   float *d_img;
   SiftPoint *d_pts;
   float *h_img;          // pinned
+  uint8_t *d_u8;         // device staging for 8-bit uploads (lazily allocated)
   SiftPoint *h_pts;      // pinned
   unsigned int *h_counters;
   bool hostResults;
@@ -956,6 +957,7 @@ int cs_extractor_destroy(cs_extractor *ex)
   if (ex->graph) cudaGraphDestroy(ex->graph);
   ex->pipe.destroy();
   if (ex->d_img) cudaFree(ex->d_img);
+  if (ex->d_u8) cudaFree(ex->d_u8);
   if (ex->d_pts) cudaFree(ex->d_pts);
   if (ex->h_img) cudaFreeHost(ex->h_img);
   if (ex->h_pts) cudaFreeHost(ex->h_pts);
@@ -1001,6 +1003,19 @@ int cs_extractor_submit_host(cs_extractor *ex, const float *h_img, double initBl
   CS_CUDA(cudaMemcpy2DAsync(ex->d_img, (size_t)ex->pitch * sizeof(float), h_img, (size_t)ex->w * sizeof(float),
                             (size_t)ex->w * sizeof(float), ex->h, cudaMemcpyHostToDevice, ex->stream));
   int r = cs_extractor_submit_device(ex, ex->d_img, ex->pitch, initBlur, thresh, lowestScale);
+  ex->hostResults = true;
+  return r;
+}
+
+int cs_extractor_submit_host_u8(cs_extractor *ex, const unsigned char *h_img, double initBlur, float thresh,
+                                float lowestScale)
+{
+  const int p8 = ialignup(ex->w, 128);
+  if (!ex->d_u8) CS_CUDA(cudaMalloc((void **)&ex->d_u8, (size_t)p8 * ex->h));
+  CS_CUDA(cudaMemcpy2DAsync(ex->d_u8, p8, h_img, ex->w, ex->w, ex->h, cudaMemcpyHostToDevice, ex->stream));
+  int r = launch_u8_to_float(ex->d_u8, p8, ex->d_img, ex->pitch, ex->w, ex->h, ex->stream);
+  if (r < 0) return r;
+  r = cs_extractor_submit_device(ex, ex->d_img, ex->pitch, initBlur, thresh, lowestScale);
   ex->hostResults = true;
   return r;
 }

@@ -58,6 +58,7 @@ int launch_scaledown(const float *src, float *dst, int w, int h, int pitch, int 
                      const Taps5 &taps, cudaStream_t st);
 int launch_scaleup(const float *src, float *dst, int w, int h, int pitch, int newpitch,
                    cudaStream_t st);
+int launch_u8_to_float(const uint8_t *src, int srcPitch, float *dst, int dstPitch, int w, int h, cudaStream_t st);
 
 // ---- detection ---------------------------------------------------------------------
 struct DetectLevel {

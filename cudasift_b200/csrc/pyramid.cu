@@ -245,4 +245,32 @@ int launch_scaleup(const float *src, float *dst, int w, int h, int pitch, int ne
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------
+// 8-bit greyscale -> float (exact), for callers that hold camera/decoder output: uploading
+// bytes moves 4x less over PCIe than the float image the reference API takes.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+u8_to_float_kernel(const uint8_t *__restrict__ src, int srcPitch, float *__restrict__ dst, int dstPitch, int w, int h)
+{
+  const int x = (blockIdx.x * 256 + threadIdx.x) * 4, y = blockIdx.y;
+  if (x >= w || y >= h) return;
+  const uint8_t *p = src + (size_t)y * srcPitch + x;
+  float *o = dst + (size_t)y * dstPitch + x;
+  if (x + 3 < w && ((srcPitch & 3) == 0) && ((dstPitch & 3) == 0)) {
+    const uchar4 v = *reinterpret_cast<const uchar4 *>(p);
+    *reinterpret_cast<float4 *>(o) = make_float4((float)v.x, (float)v.y, (float)v.z, (float)v.w);
+  } else {
+    for (int i = 0; i < 4 && x + i < w; i++) o[i] = (float)p[i];
+  }
+}
+
+int launch_u8_to_float(const uint8_t *src, int srcPitch, float *dst, int dstPitch, int w, int h, cudaStream_t st)
+{
+  dim3 grid(idivup(idivup(w, 4), 256), h);
+  u8_to_float_kernel<<<grid, 256, 0, st>>>(src, srcPitch, dst, dstPitch, w, h);
+  count_launch();
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace cs

@@ -110,6 +110,10 @@ int cs_extractor_submit_device(cs_extractor *ex, const float *d_img, int pitch,
  * count and records into the extractor's pinned result buffer. */
 int cs_extractor_submit_host(cs_extractor *ex, const float *h_img,
                              double initBlur, float thresh, float lowestScale);
+/* Same for an 8-bit greyscale image (width*height bytes, packed): 4x less PCIe traffic; the
+ * conversion to float on the device is exact, so results equal submit_host of the float image. */
+int cs_extractor_submit_host_u8(cs_extractor *ex, const unsigned char *h_img,
+                                double initBlur, float thresh, float lowestScale);
 /* One image, synchronously, with CUDA events at the stage boundaries of the extractor's
  * stream: out_ms = {LowPass, ScaleDown chain, detect (blur+DoG+extrema), describe
  * (orientation+descriptor), total}.  Returns numPts. */

@@ -130,3 +130,30 @@ def test_edge_cases(cs):
     assert len(few) == 50
     flat = np.full((64, 64), 100.0, np.float32)
     assert len(_extract(cs, flat)) == 0
+
+
+def test_extractor_pipeline_and_u8_upload(cs):
+    """The pipelined extractor (CUDA-graph submit path after the second call) returns what the
+    synchronous call returns; an 8-bit upload gives the same records as its float image."""
+    import ctypes
+    arr8 = np.clip(np.rint(synth_image(640, 480, seed=41)), 0, 255).astype(np.uint8)
+    arrf = arr8.astype(np.float32)
+    want = canon(_extract(cs, arrf, thresh=3.0))
+    ex = cs.Extractor(640, 480, 5, 8192)
+    ex.host_image()[:] = arrf
+    got = []
+    for rep in range(4):                      # reps >= 2 run through the captured graph
+        ex.submit_host(ex.host_image().ctypes.data, 1.0, 3.0, 0.0)
+        n = ex.wait()
+        got.append(canon(ex.host_points(n).copy()))
+    p8 = cs.lib().cs_host_alloc_pinned(640 * 480)
+    ctypes.memmove(p8, arr8.ctypes.data, 640 * 480)
+    ex.submit_host_u8(p8, 1.0, 3.0, 0.0)
+    n = ex.wait()
+    got.append(canon(ex.host_points(n).copy()))
+    cs.lib().cs_host_free_pinned(p8)
+    for g in got:
+        assert len(g) == len(want)
+        for f in ("xpos", "ypos", "scale", "orientation", "subsampling", "data"):
+            assert np.array_equal(g[f], want[f]), f
+    ex.close()
