@@ -30,7 +30,8 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 W, H, OCTAVES, INIT_BLUR, THRESH, MAX_PTS = 1920, 1080, 5, 1.0, 3.0, 32768
-LEVEL_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of detect_kernel per launch (ncu --set full, 1080p, profiles/)
+DETECT_DRAM_BYTES = 11.10e6
 
 
 def level_sizes(w=W, h=H, n=OCTAVES):
@@ -207,7 +208,7 @@ def run_product(args):
         p = L.cs_host_alloc_pinned(W * H * 4)
         ctypes.memmove(p, imgs[i % len(imgs)].ctypes.data, W * H * 4)
         himgs.append(p)
-    e2e_images = max(B, 16) * max(1, args.steps // 2)
+    e2e_images = max(B, 16) * max(1, min(args.steps, 100) // 2)
 
     def run_e2e(n):
         busy = [False] * S
@@ -301,7 +302,8 @@ def run_product(args):
         ach = detect_bytes / (detect_ms * 1e-3) / 1e9
         out["roofline"] = {"bound": "hbm", "kernel": "detect_kernel (8-scale blur + DoG + 3x3x3 extrema, all octaves)",
                            "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                           "traffic": None, "peak_source": how, "algorithmic_bytes_per_launch": detect_bytes,
+                           "traffic": DETECT_DRAM_BYTES, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one "
+                           "ncu --set full capture of detect_kernel (profiles/r01_prof_detect.txt)", "peak_source": how, "algorithmic_bytes_per_launch": detect_bytes,
                            "avg_launch_ms": round(float(detect_ms), 4),
                            "stage_ms": {"lowpass": round(float(lowpass_ms), 4), "scaledown_x4": round(float(sd_ms), 4),
                                         "detect": round(float(detect_ms), 4), "describe": round(float(describe_ms), 4),
@@ -452,7 +454,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per step per GPU")

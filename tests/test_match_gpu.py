@@ -75,3 +75,33 @@ def test_match_device_api(cs):
     assert np.array_equal(dev["data"], s1["data"])        # descriptors untouched
     d1.numPts = 0
     assert cs.MatchSiftData(d1, d2) == 0.0                # matching.cu:1095-1096
+
+
+def test_match_large_tensor_equals_exact(cs):
+    """Beyond the sizes the CPU oracle can check quickly: the tensor path against the exact
+    SIMT path (itself bit-identical to the oracle/reference at smaller sizes)."""
+    n1, n2 = 20000, 24000
+    s1, s2 = synth_descriptors(n1, 21, sift_like=True), synth_descriptors(n2, 22, sift_like=True)
+    a, _ = cs.match_host(s1, s2, mode=1)
+    b, _ = cs.match_host(s1, s2, mode=2)
+    _eq(b, a, "tensor vs exact %dx%d" % (n1, n2))
+    st = cs.match_stats()
+    assert st[3] == 2 and st[2] < 0.01 * n1, st            # tensor path taken, <1 % rows needed the fallback
+
+
+def test_match_extracted_descriptors(cs):
+    """End to end on real descriptors (many zeros, clamped at 0.2): ExtractSift on two views of a
+    scene, MatchSiftData on both paths, identical output; most points find their counterpart."""
+    from cudasift_b200.synth import synth_image
+    img = synth_image(1280, 960, seed=77)
+    shifted = np.roll(img, (7, 11), axis=(0, 1))
+    p1, p2 = cs.extract_host(img, thresh=3.0), cs.extract_host(shifted, thresh=3.0)
+    assert len(p1) > 500 and len(p2) > 500
+    a, _ = cs.match_host(p1, p2, mode=1)
+    b, _ = cs.match_host(p1, p2, mode=2)
+    _eq(b, a, "extracted descriptors")
+    _eq(a, oracle.match(p1, p2, threads=8), "exact path vs oracle")
+    good = (a["score"] > 0.9) & (a["ambiguity"] < 0.9)
+    dx, dy = a["match_xpos"][good] - a["xpos"][good], a["match_ypos"][good] - a["ypos"][good]
+    assert good.sum() > 0.5 * len(p1)
+    assert np.median(np.abs(dx - 11)) < 0.5 and np.median(np.abs(dy - 7)) < 0.5
