@@ -67,6 +67,7 @@ def lib():
         "cs_match_host": (ip, [vp, ip, vp, ip, ip, c.POINTER(c.c_double)]),
         "cs_match_stats": (ip, [c.POINTER(c.c_ulonglong)]),
         "cs_find_homography": (ip, [vp, ip, vp, c.POINTER(c.c_int), ip, fp, fp, fp, c.POINTER(c.c_double)]),
+        "cs_improve_homography": (ip, [vp, ip, vp, ip, fp, fp, fp, c.POINTER(c.c_int)]),
         "cs_lowpass": (ip, [vp, vp, ip, ip, ip, fp]),
         "cs_scaledown": (ip, [vp, vp, ip, ip, ip, ip]),
         "cs_scaleup": (ip, [vp, vp, ip, ip, ip, ip]),
@@ -247,6 +248,17 @@ def FindHomography(data, numLoops=1000, minScore=0.85, maxAmbiguity=0.95, thresh
     _check(lib().cs_find_homography(data.d_data, data.numPts, _ptr(H), ctypes.byref(n), int(numLoops), float(minScore),
                                     float(maxAmbiguity), float(thresh), ctypes.byref(ms)), "FindHomography")
     return H.reshape(3, 3), n.value, ms.value
+
+
+def ImproveHomography(records, homography, numLoops=5, minScore=0.0, maxAmbiguity=0.80, thresh=3.0):
+    """geomFuncs.cpp:6-72 on a host record array (modified in place: match_error).  Returns
+    (refined 3x3 homography, numFit).  Defaults are the demo's (mainSift.cpp:78)."""
+    assert records.dtype == SIFT_DTYPE and records.flags.c_contiguous
+    H = np.ascontiguousarray(np.asarray(homography, np.float32).reshape(9)).copy()
+    n = ctypes.c_int(0)
+    _check(lib().cs_improve_homography(_ptr(records), len(records), _ptr(H), int(numLoops), float(minScore),
+                                       float(maxAmbiguity), float(thresh), ctypes.byref(n)), "ImproveHomography")
+    return H.reshape(3, 3), n.value
 
 
 def match_stats():

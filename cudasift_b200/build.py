@@ -22,7 +22,7 @@ REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 REF_LIB = os.path.join(REF_DIR, "libcudasift_ref.so")
 REFERENCE_SRC = "/root/reference"
 
-SOURCES = ["api.cu", "pyramid.cu", "detect.cu", "describe.cu", "match.cu", "match_tc.cu", "homography.cu"]
+SOURCES = ["api.cu", "pyramid.cu", "detect.cu", "describe.cu", "match.cu", "match_tc.cu", "homography.cu", "geom.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-shared"]
 

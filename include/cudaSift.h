@@ -60,5 +60,9 @@ double MatchSiftData(SiftData &data1, SiftData &data2);
 // matching.cu:1000-1087 (RANSAC homography; outside the round-1 hot path).
 double FindHomography(SiftData &data, float *homography, int *numMatches, int numLoops = 1000,
                       float minScore = 0.85f, float maxAmbiguity = 0.95f, float thresh = 5.0f);
+// geomFuncs.cpp:6-72 (declared by the caller in the reference, mainSift.cpp:16).  Host-side
+// refinement over data.h_data; fills match_error, returns the number of matches within thresh.
+int ImproveHomography(SiftData &data, float *homography, int numLoops, float minScore, float maxAmbiguity,
+                      float thresh);
 
 #endif

@@ -82,6 +82,12 @@ int cs_match_stats(unsigned long long out[4]);
 int cs_find_homography(void *d_pts, int numPts, float *homography, int *numMatches, int numLoops,
                        float minScore, float maxAmbiguity, float thresh, double *ms);
 
+/* ImproveHomography (geomFuncs.cpp:6-72): host-side iterated least-squares refinement over the
+ * HOST records (the reference runs it on data.h_data with OpenCV); fills match_error of every
+ * record and overwrites homography[0..8]; *numFit = matches within thresh. */
+int cs_improve_homography(void *h_pts, int numPts, float *homography, int numLoops, float minScore,
+                          float maxAmbiguity, float thresh, int *numFit);
+
 /* ---- stage-level entry points (reference: cudaSiftH.h:11-22), used by parity tests ---- */
 int cs_lowpass(const float *d_src, float *d_dst, int width, int height, int pitch, float sigma);
 int cs_scaledown(const float *d_src, float *d_dst, int width, int height, int pitch, int newpitch);

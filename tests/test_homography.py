@@ -75,3 +75,32 @@ def test_find_homography_vs_reference(cs, reflib):
     Hg, ng, _ = cs.FindHomography(sd, 2000, 0.85, 0.95, 4.0, seed=11)
     assert abs(ng - nr.value) <= max(2, 0.005 * nr.value), (ng, nr.value)
     assert np.allclose(Hg.ravel()[:8], Hr[:8], rtol=2e-3, atol=1e-5), (Hg, Hr)
+
+
+def test_improve_homography_host():
+    """ImproveHomography (geomFuncs.cpp:6-72) is host code in the reference and here: product (own 8x8
+    Cholesky) against the numpy restatement, and against the planted geometry."""
+    import cudasift_b200 as cs
+    from oracle.geom import improve_homography
+    p, bad = planted(n=900, seed=11, noise=0.25)
+    # a deliberately rough start (what a short RANSAC would hand over)
+    H0 = H_TRUE.copy(); H0[0, 2] += 1.5; H0[1, 2] -= 1.0; H0[0, 0] *= 1.001
+    H0 = (H0 * 1.7).astype(np.float32)                       # not normalised: [8] != 1 on input
+    for loops, mins, maxa, thr in ((5, 0.0, 0.80, 3.0), (1, 0.85, 0.95, 5.0), (8, 0.0, 1.0, 2.0)):
+        q = p.copy()
+        Hp, nfit = cs.ImproveHomography(q, H0, loops, mins, maxa, thr)
+        Ho, nfo, erro = improve_homography(p, H0, loops, mins, maxa, thr)
+        assert nfit == nfo, (nfit, nfo)
+        assert np.allclose(Hp.reshape(9), Ho, rtol=1e-5, atol=1e-7), (Hp, Ho)
+        assert np.allclose(q["match_error"], erro, rtol=1e-3, atol=1e-3)
+        assert Hp[2, 2] == 1.0
+        assert nfit >= 0.95 * (~bad).sum()
+    pts = np.array([[100.0, 200.0, 1.0], [1000.0, 800.0, 1.0], [640.0, 480.0, 1.0]]).T
+    a, b = Hp.astype(np.float64) @ pts, H_TRUE @ pts
+    assert np.max(np.abs(a[:2] / a[2] - b[:2] / b[2])) < 0.15     # refinement beats the 1.5 px start
+    # no eligible matches: singular normal equations -> zero solution, match_error still filled
+    q = p.copy()
+    Hz, nz = cs.ImproveHomography(q, H0, 2, 2.0, 0.0, 3.0)
+    assert np.array_equal(Hz.reshape(9)[:8], np.zeros(8, np.float32)) and Hz[2, 2] == 1.0
+    Hzo, nzo, _ = improve_homography(p, H0, 2, 2.0, 0.0, 3.0)
+    assert nz == nzo and np.array_equal(Hz.reshape(9), Hzo)
