@@ -100,8 +100,24 @@ def build_reference(force=False):
     return REF_LIB
 
 
+DEMO = os.path.join(LIBDIR, "sift_demo")
+
+
+def build_demo(force=False):
+    """examples/sift_demo.cpp: a plain g++ caller of the drop-in headers, linked against the library."""
+    src = os.path.join(ROOT, "examples", "sift_demo.cpp")
+    lib = build_library()
+    if not force and _newer(DEMO, [src, lib]):
+        return DEMO
+    if shutil.which("g++") is None:
+        return DEMO if os.path.exists(DEMO) else None
+    _run(["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), src, "-L" + LIBDIR,
+          "-lcudasift_b200", "-Wl,-rpath,$ORIGIN", "-o", DEMO])
+    return DEMO
+
+
 def build_all(force=False, verbose=False):
-    return build_library(force, verbose), build_oracle(force), build_reference(force)
+    return build_library(force, verbose), build_oracle(force), build_reference(force), build_demo(force)
 
 
 if __name__ == "__main__":

@@ -1,0 +1,46 @@
+"""examples/sift_demo.cpp: a g++-compiled caller of include/cudaSift.h + cudaImage.h (the role of the
+reference's mainSift.cpp:25-93), run end to end and cross-checked with the ctypes API."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from cudasift_b200 import build as _build
+from cudasift_b200.synth import synth_image
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _write_pgm(path, img):
+    a = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    with open(path, "wb") as f:
+        f.write(b"P5\n# synthetic\n%d %d\n255\n" % (a.shape[1], a.shape[0]))
+        f.write(a.tobytes())
+    return a.astype(np.float32)
+
+
+@pytest.mark.gpu
+def test_demo_program(cs, tmp_path):
+    demo = _build.build_demo()
+    assert demo and os.path.exists(demo)
+    left = synth_image(1280, 960, seed=5)
+    right = np.roll(left, (9, -13), axis=(0, 1))
+    l8 = _write_pgm(str(tmp_path / "l.pgm"), left)
+    r8 = _write_pgm(str(tmp_path / "r.pgm"), right)
+    out = str(tmp_path / "marked.pgm")
+    r = subprocess.run([demo, str(tmp_path / "l.pgm"), str(tmp_path / "r.pgm"), "--thresh", "3.0", "--repeat", "3", "--out", out,
+                        "--print", "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout
+    m = re.search(r"Number of original features: (\d+) (\d+)", r.stdout)
+    n1, n2 = int(m.group(1)), int(m.group(2))
+    assert n1 == len(cs.extract_host(l8, thresh=3.0)) and n2 == len(cs.extract_host(r8, thresh=3.0))
+    m = re.search(r"Number of matching features: (\d+) (\d+)", r.stdout)
+    numFit, numMatches = int(m.group(1)), int(m.group(2))
+    assert numFit > 50 and numMatches > 50, r.stdout
+    H = np.array([float(v) for v in re.search(r"Homography:\s+((?:\S+\s+){9})", r.stdout).group(1).split()]).reshape(3, 3)
+    assert abs(H[0, 2] + 13) < 0.5 and abs(H[1, 2] - 9) < 0.5 and abs(H[0, 0] - 1) < 0.01, H   # the planted shift
+    with open(out, "rb") as f:
+        assert f.read(2) == b"P5"
+    assert os.path.getsize(out) > 1280 * 960
