@@ -208,7 +208,7 @@ int Pipeline::enqueue(const float *d_img, int pitch, double initBlur, float thre
     L.lowestScale = lowestScale / L.subsampling;                           // cudaSiftH.cu:213
     const float *k = lapTaps + (numOctaves - i) * 12 * 16;                 // octave index, :161,:1766
     for (int s = 0; s < CS_LAPLACE_S; s++)
-      for (int j = 0; j < 5; j++) L.taps.k[s][j] = k[16 * s + j];
+      for (int j = 0; j < 5; j++) L.taps.set(s, j, k[16 * s + j]);
   }
   dp.numLevels = nl; dp.totalTiles = tiles;
   dp.thresh = thresh; dp.edgeLimit = 10.0f; dp.factor = 1.0f / CS_NUM_SCALES;   // cudaSiftH.cu:213
@@ -842,7 +842,7 @@ int cs_dog_planes(const float *d_base, float *d_dog, int w, int h, int pitch, in
   laplace_taps(numOctaves, 0.0f, taps);
   LaplaceTaps lt;
   for (int s = 0; s < CS_LAPLACE_S; s++)
-    for (int j = 0; j < 5; j++) lt.k[s][j] = taps[octave * 12 * 16 + 16 * s + j];
+    for (int j = 0; j < 5; j++) lt.set(s, j, taps[octave * 12 * 16 + 16 * s + j]);
   int r = launch_dog_planes(d_base, d_dog, w, h, pitch, lt, c->stream);
   if (r < 0) return r;
   CS_CUDA(cudaStreamSynchronize(c->stream));

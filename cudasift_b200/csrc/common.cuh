@@ -49,7 +49,12 @@ void laplace_taps(int numOctaves, float initBlur, float *kernel); // cudaSiftH.c
 
 struct Taps9 { float k[9]; };
 struct Taps5 { float k[5]; };
-struct LaplaceTaps { float k[CS_LAPLACE_S][5]; };   // [scale][tap], tap 0 = centre
+// [scale][tap], tap 0 = centre; every tap is stored twice (k,k): the detector consumes it as the
+// uniform operand of a packed fma.rn.f32x2
+struct LaplaceTaps {
+  float2 k[CS_LAPLACE_S][5];
+  void set(int s, int j, float v) { k[s][j].x = v; k[s][j].y = v; }
+};
 
 // ---- pyramid ----------------------------------------------------------------------
 int launch_lowpass(const float *src, int srcPitch, float *dst, int dstPitch, int w, int h,
