@@ -49,6 +49,7 @@ def lib():
         "cs_version": (c.c_char_p, []),
         "cs_init": (ip, [ip]),
         "cs_launch_count": (c.c_ulonglong, []),
+        "cs_set_tuning": (ip, [c.c_char_p, ip]),
         "cs_extract_launches_per_image": (ip, [ip, ip]),
         "cs_device_alloc": (vp, [c.c_size_t]),
         "cs_device_free": (ip, [vp]),

@@ -212,7 +212,7 @@ int Pipeline::enqueue(const float *d_img, int pitch, double initBlur, float thre
   }
   dp.numLevels = nl; dp.totalTiles = tiles;
   dp.thresh = thresh; dp.edgeLimit = 10.0f; dp.factor = 1.0f / CS_NUM_SCALES;   // cudaSiftH.cu:213
-  dp.pts = d_pts; dp.counters = d_counters; dp.maxPts = maxPts;
+  dp.pts = d_pts; dp.counters = d_counters; dp.maxPts = maxPts; dp.dbgSkip = g_detect_skip;
   if ((r = launch_detect(dp, st)) < 0) return r;
   if (ev) cudaEventRecord(ev[3], st);
 
@@ -664,6 +664,14 @@ extern "C" {
 const char *cs_last_error(void) { return cs::g_err; }
 const char *cs_version(void) { return "cudasift_b200 0.1 (sm_100a)"; }
 unsigned long long cs_launch_count(void) { return cs::g_launches; }
+
+int cs_set_tuning(const char *key, int value)
+{
+  if (key && strcmp(key, "detect_variant") == 0) { cs::g_detect_variant = value; return 0; }
+  if (key && strcmp(key, "detect_skip") == 0) { cs::g_detect_skip = value; return 0; }
+  cs::set_error("cs_set_tuning: unknown key");
+  return CS_E_ARG;
+}
 
 int cs_extract_launches_per_image(int numOctaves, int scaleUp)
 { // lowpass + (numOctaves-1) scaledown + detect + describe (+ scaleup + rescale)

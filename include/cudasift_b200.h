@@ -33,6 +33,9 @@ const char *cs_version(void);
 int cs_init(int device);
 /* Number of kernels this library has launched so far in this process. */
 unsigned long long cs_launch_count(void);
+/* Tuning hook (benchmarks only): key "detect_variant" selects one of the compiled detector
+ * configurations for pipelines created afterwards.  Returns 0, or CS_E_ARG for an unknown key. */
+int cs_set_tuning(const char *key, int value);
 /* Number of launches one steady-state cs_extractor_submit_* / cs_match issues. */
 int cs_extract_launches_per_image(int numOctaves, int scaleUp);
 
