@@ -113,6 +113,8 @@ struct Pipeline {
   float *upImg = nullptr;
   cudaTextureObject_t tex[CS_MAX_LEVELS] = {};
   unsigned int *d_counters = nullptr;   // [0] primaries found, [1] total incl. secondaries
+  uint2 *d_tiles = nullptr;             // detector tile list (level, x0, y0), all levels
+  int numTiles = 0;
   float lapTaps[8 * 12 * 16];
   Taps5 sdTaps;
   int describeBlocks = 0;
@@ -154,6 +156,25 @@ int Pipeline::init(int w, int h, int octaves, bool up, float *arenaPtr)
     if (r < 0) return r;
   }
   CS_CUDA(cudaMalloc((void **)&d_counters, 4 * sizeof(unsigned int)));
+  {
+    // coarsest level first: its tiles carry the most extrema candidates, so the persistent CTAs
+    // finish on the light tiles of the finest level
+    std::vector<uint2> tl;
+    int nl = 0, idx[CS_MAX_LEVELS];
+    for (int i = 0; i < numLevels; i++) idx[i] = (lw[i] < 3 || lh[i] < 3) ? -1 : nl++;   // no interior pixel -> no extrema
+    for (int i = numLevels - 1; i >= 0; i--) {
+      if (idx[i] < 0) continue;
+      const int tx = idivup(lw[i] - 2, CS_DETECT_TILE_W), ty = idivup(lh[i] - 2, CS_DETECT_TILE_H);
+      for (int y = 0; y < ty; y++)
+        for (int x = 0; x < tx; x++)
+          tl.push_back(make_uint2((unsigned)idx[i] | ((unsigned)(x * CS_DETECT_TILE_W) << 8), (unsigned)(y * CS_DETECT_TILE_H)));
+    }
+    numTiles = (int)tl.size();
+    if (numTiles > 0) {
+      CS_CUDA(cudaMalloc((void **)&d_tiles, tl.size() * sizeof(uint2)));
+      CS_CUDA(cudaMemcpy(d_tiles, tl.data(), tl.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+    }
+  }
   memset(lapTaps, 0, sizeof(lapTaps));
   laplace_taps(octaves, 0.0f, lapTaps);           // cudaSiftH.cu:110
   scaledown_taps(0.5f, sdTaps.k);                 // cudaSiftH.cu:157
@@ -169,6 +190,7 @@ void Pipeline::destroy()
   for (int i = 0; i < CS_MAX_LEVELS; i++)
     if (tex[i]) { cudaDestroyTextureObject(tex[i]); tex[i] = 0; }
   if (d_counters) { cudaFree(d_counters); d_counters = nullptr; }
+  if (d_tiles) { cudaFree(d_tiles); d_tiles = nullptr; }
   if (ownArena && arena) cudaFree(arena);
   arena = nullptr;
 }
@@ -201,7 +223,7 @@ int Pipeline::enqueue(const float *d_img, int pitch, double initBlur, float thre
     if (lw[i] < 3 || lh[i] < 3) continue;          // no interior pixel -> no extrema possible
     DetectLevel &L = dp.lev[nl++];
     L.img = lev[i]; L.w = lw[i]; L.h = lh[i]; L.pitch = lp[i];
-    L.tilesX = idivup(lw[i] - 2, 62); L.tilesY = idivup(lh[i] - 2, 14);
+    L.tilesX = idivup(lw[i] - 2, CS_DETECT_TILE_W); L.tilesY = idivup(lh[i] - 2, CS_DETECT_TILE_H);
     L.tileBase = tiles;
     tiles += L.tilesX * L.tilesY;
     L.subsampling = (float)(1 << i);
@@ -210,7 +232,8 @@ int Pipeline::enqueue(const float *d_img, int pitch, double initBlur, float thre
     for (int s = 0; s < CS_LAPLACE_S; s++)
       for (int j = 0; j < 5; j++) L.taps.set(s, j, k[16 * s + j]);
   }
-  dp.numLevels = nl; dp.totalTiles = tiles;
+  dp.numLevels = nl; dp.totalTiles = tiles; dp.tiles = d_tiles;
+  if (tiles != numTiles) { set_error("detector tile list out of sync"); return CS_E_ARG; }
   dp.thresh = thresh; dp.edgeLimit = 10.0f; dp.factor = 1.0f / CS_NUM_SCALES;   // cudaSiftH.cu:213
   dp.pts = d_pts; dp.counters = d_counters; dp.maxPts = maxPts; dp.dbgSkip = g_detect_skip;
   if ((r = launch_detect(dp, st)) < 0) return r;

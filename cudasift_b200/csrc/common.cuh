@@ -79,6 +79,7 @@ struct DetectParams {
   DetectLevel lev[CS_MAX_LEVELS];
   int numLevels;
   int totalTiles;
+  const uint2 *tiles;       // per tile: x = level | x0 << 8, y = y0 (built once per pipeline)
   float thresh, edgeLimit, factor;
   SiftPoint *pts;
   unsigned int *counters;   // [0] detected (primaries), [1] total incl. secondaries
@@ -88,6 +89,8 @@ struct DetectParams {
 extern int g_detect_skip;      // tuning (cs_set_tuning "detect_skip")
 extern int g_detect_variant;   // tuning (cs_set_tuning "detect_variant")
 int launch_detect(const DetectParams &p, cudaStream_t st);
+#define CS_DETECT_TILE_W 62   // interior (tested) pixels per detector tile
+#define CS_DETECT_TILE_H 14
 int launch_dog_planes(const float *base, float *dog, int w, int h, int pitch,
                       const LaplaceTaps &taps, cudaStream_t st);
 

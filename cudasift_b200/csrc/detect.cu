@@ -322,15 +322,9 @@ __device__ __noinline__ void refine(const float *pl, int r, int d, int gx, int g
 struct TilePos { int level, x0, y0; };
 __device__ __forceinline__ TilePos decode_tile(const DetectParams &P, int t)
 {
+  const uint2 e = __ldg(P.tiles + t);
   TilePos tp;
-  tp.level = 0;                        // levels are listed coarsest-last
-#pragma unroll 1
-  for (int l = 1; l < P.numLevels; l++)
-    if (t >= P.lev[l].tileBase) tp.level = l;
-  const DetectLevel &L = P.lev[tp.level];
-  const int tile = t - L.tileBase;
-  const int by = tile / L.tilesX, bx = tile - by * L.tilesX;
-  tp.x0 = bx * (DT_W - 2); tp.y0 = by * (DT_H - 2);
+  tp.level = e.x & 0xff; tp.x0 = e.x >> 8; tp.y0 = e.y;
   return tp;
 }
 
@@ -345,13 +339,15 @@ detect_kernel(const __grid_constant__ DetectParams P)
   // the candidate list (at most 62*14 entries) reuses the vertical-result buffer once the blur is over
   unsigned short *s_list = reinterpret_cast<unsigned short *>(s_v);
   static_assert((DT_H - 2) * (DT_W - 2) * 2 <= DT_SM_V * 8, "candidate list fits into the vertical-result buffer");
-  __shared__ int s_cnt, s_kn;
+  __shared__ int s_cnt, s_kn, s_next;
   __shared__ Keypoint s_kq[DT_KQ];
   const float thresh = P.thresh;
   const float *dogf = reinterpret_cast<const float *>(s_dog);
   const int skip = P.dbgSkip;
 
   int t = blockIdx.x;
+  unsigned int req = 0;
+  if (threadIdx.x == 0) req = gridDim.x + atomicAdd(&P.counters[2], 1u);
   TilePos tp = decode_tile(P, t);
   if (threadIdx.x == 0) { s_cnt = 0; s_kn = 0; }
   if (!(skip & 1)) tile_prefetch<DT_THREADS>(s_in, P.lev[tp.level].img, P.lev[tp.level].w, P.lev[tp.level].h, P.lev[tp.level].pitch, tp.x0, tp.y0);
@@ -367,11 +363,19 @@ detect_kernel(const __grid_constant__ DetectParams P)
     unsigned int slot = 0;
     if ((int)threadIdx.x < nkq) slot = atomicAdd(&P.counters[0], 1u);
 
-    const int tn = t + gridDim.x;
-    const bool more = tn < P.totalTiles;
+    // dynamic tile scheduler, one request ahead: publish the index requested during the previous
+    // tile (the barriers of the blur make it visible before mid()), request the one after
+    if (threadIdx.x == 0) {
+      s_next = (int)req;
+      req = gridDim.x + atomicAdd(&P.counters[2], 1u);
+    }
+    int tn = 0;
+    bool more = false;
     TilePos tpn = tp;
     const unsigned int mask = dog_tile<DT_THREADS, NC, VR>(L.w, L.h, x0, y0, L.taps, s_in, s_v, s_dog, thresh, skip, [&]() {
       // the staging area is free: start the next tile's copies, retire the parked keypoints
+      tn = s_next;
+      more = tn < P.totalTiles;
       if (more) {
         tpn = decode_tile(P, tn);
         const DetectLevel &Ln = P.lev[tpn.level];
@@ -383,30 +387,51 @@ detect_kernel(const __grid_constant__ DetectParams P)
     list_append<NC>(mask, s_list, &s_cnt);
     __syncthreads();
 
-    // 3x3x3 extrema, only on the pixels the blur pass flagged (|DoG| > thresh at some scale);
-    // one work item per (flagged pixel, scale)
+    // 3x3x3 extrema, only on the pixels the blur pass flagged (|DoG| > thresh at some scale); one work
+    // item per (flagged pixel, scale).  Sparse tiles (the finest octave: ~2 flagged pixels per tile)
+    // give a warp per item, lane j < 27 holding neighbour j of the 3x3x3 cube -- a short critical path;
+    // dense tiles (coarse octaves: up to 20 % of the pixels) give a thread per item.
     const int nitems = (skip & 8) ? 0 : s_cnt * CS_NUM_SCALES;
-    for (int i = threadIdx.x; i < nitems; i += DT_THREADS) {
-      const int ci = i / CS_NUM_SCALES, sc = i - ci * CS_NUM_SCALES;
-      const int rd = s_list[ci];
-      const int r = rd / DT_W, d = rd - r * DT_W;
-      const float *pl = dogf + sc * (DT_HP * DT_W * 2);
-      const float c = pl[DT_HP * DT_W * 2 + dog_index(0, r, d)];
-      if (!(fabsf(c) > thresh)) continue;
-      bool mx = true, mn = true;
+    if (nitems <= 4 * (DT_THREADS / 32)) {
+      const int lane = threadIdx.x & 31;
+      const int pz = lane / 9, py = (lane - 9 * pz) / 3, px = lane - 9 * pz - 3 * py;
+      for (int i = threadIdx.x >> 5; i < nitems; i += DT_THREADS / 32) {
+        const int ci = i / CS_NUM_SCALES, sc = i - ci * CS_NUM_SCALES;
+        const int rd = s_list[ci];
+        const int r = rd / DT_W, d = rd - r * DT_W;
+        const float *pl = dogf + sc * (DT_HP * DT_W * 2);
+        float tt = 0.0f;
+        if (lane < 27) tt = pl[pz * (DT_HP * DT_W * 2) + dog_index(0, r + py - 1, d + px - 1)];
+        const float c = __shfl_sync(0xffffffffu, tt, 13);          // the candidate itself: (1,1,1)
+        if (!(fabsf(c) > thresh)) continue;
+        const bool other = lane < 27 && lane != 13;
+        const bool mx = __all_sync(0xffffffffu, !other || c > tt);
+        const bool mn = __all_sync(0xffffffffu, !other || c < tt);
+        if ((c > 0.0f ? mx : mn) && lane == 0 && !(skip & 16)) refine(pl, r, d, x0 + d, y0 + r, sc, L, P, s_kq, &s_kn);
+      }
+    } else {
+      for (int i = threadIdx.x; i < nitems; i += DT_THREADS) {
+        const int ci = i / CS_NUM_SCALES, sc = i - ci * CS_NUM_SCALES;
+        const int rd = s_list[ci];
+        const int r = rd / DT_W, d = rd - r * DT_W;
+        const float *pl = dogf + sc * (DT_HP * DT_W * 2);
+        const float c = pl[DT_HP * DT_W * 2 + dog_index(0, r, d)];
+        if (!(fabsf(c) > thresh)) continue;
+        bool mx = true, mn = true;
 #pragma unroll
-      for (int dy = 0; dy < 3; dy++)
+        for (int dy = 0; dy < 3; dy++)
 #pragma unroll
-        for (int dx = 0; dx < 3; dx++) {
-          const int o = dog_index(0, r + dy - 1, d + dx - 1);
+          for (int dx = 0; dx < 3; dx++) {
+            const int o = dog_index(0, r + dy - 1, d + dx - 1);
 #pragma unroll
-          for (int p = 0; p < 3; p++)
-            if (p != 1 || dy != 1 || dx != 1) {
-              const float tt = pl[p * (DT_HP * DT_W * 2) + o];
-              mx = mx && (c > tt); mn = mn && (c < tt);
-            }
-        }
-      if ((c > 0.0f ? mx : mn) && !(skip & 16)) refine(pl, r, d, x0 + d, y0 + r, sc, L, P, s_kq, &s_kn);
+            for (int p = 0; p < 3; p++)
+              if (p != 1 || dy != 1 || dx != 1) {
+                const float tt = pl[p * (DT_HP * DT_W * 2) + o];
+                mx = mx && (c > tt); mn = mn && (c < tt);
+              }
+          }
+        if ((c > 0.0f ? mx : mn) && !(skip & 16)) refine(pl, r, d, x0 + d, y0 + r, sc, L, P, s_kq, &s_kn);
+      }
     }
     if (!more) break;
     t = tn; tp = tpn;
