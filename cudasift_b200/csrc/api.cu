@@ -402,6 +402,7 @@ static int match_sync(SiftPoint *d_s1, int n1, SiftPoint *d_s2, int n2, SiftPoin
   CS_CUDA(cudaStreamSynchronize(c->stream));
   float t = 0; cudaEventElapsedTime(&t, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
+  if (useTensor) match_tensor_stats(c->matchStats);
   if (ms) *ms = t;
   return 0;
 }

@@ -117,6 +117,7 @@ int match_exact(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_t
 int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_t st,
                  unsigned long long stats[4]);
 bool match_tensor_supported();
+void match_tensor_stats(unsigned long long stats[4]);   // after a synchronize
 
 inline int idivup(int a, int b) { return (a + b - 1) / b; }
 inline int ialignup(int a, int b) { return (a % b != 0) ? (a - a % b + b) : a; }

@@ -37,8 +37,10 @@ __device__ __forceinline__ void part_update(PartState &s, float sc, int p2)
 // fallback of the tensor-core path for rows it could not certify.
 __global__ void __launch_bounds__(MX_THREADS)
 match_exact_kernel(SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ sift2, int n1, int n2,
-                   const int *__restrict__ rows, const unsigned int *__restrict__ nrows)
+                   const int *__restrict__ rows, const unsigned int *__restrict__ nrows,
+                   const unsigned int *__restrict__ gate)
 {
+  if (gate && *gate == 0) return;      // device-side switch: the tensor path's "inputs out of range" flag
   __shared__ float4 s_a[MX_ROWS * MX_LD];
   __shared__ float4 s_b[MX_COLS * MX_LD];
   const int tid = threadIdx.x;
@@ -129,7 +131,17 @@ match_exact_kernel(SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ 
 int match_exact(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_t st)
 {
   if (n1 <= 0) return 0;
-  match_exact_kernel<<<idivup(n1, MX_ROWS), MX_THREADS, 0, st>>>(s1, s2, n1, n2, nullptr, nullptr);
+  match_exact_kernel<<<idivup(n1, MX_ROWS), MX_THREADS, 0, st>>>(s1, s2, n1, n2, nullptr, nullptr, nullptr);
+  count_launch();
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// full exact scan that only runs if *gate != 0 (decided on the device, no host round trip)
+int match_exact_gated(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, const unsigned int *gate, cudaStream_t st)
+{
+  if (n1 <= 0) return 0;
+  match_exact_kernel<<<idivup(n1, MX_ROWS), MX_THREADS, 0, st>>>(s1, s2, n1, n2, nullptr, nullptr, gate);
   count_launch();
   CS_CUDA(cudaGetLastError());
   return 0;
@@ -138,7 +150,7 @@ int match_exact(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_t
 int match_exact_rows(SiftPoint *s1, const SiftPoint *s2, int n2, const int *rows, const unsigned int *nrows,
                      cudaStream_t st)
 {
-  match_exact_kernel<<<128, MX_THREADS, 0, st>>>(s1, s2, 0, n2, rows, nrows);
+  match_exact_kernel<<<128, MX_THREADS, 0, st>>>(s1, s2, 0, n2, rows, nrows, nullptr);
   count_launch();
   CS_CUDA(cudaGetLastError());
   return 0;
