@@ -11,6 +11,6 @@ timeout 600 $NCU --set full --import-source on -k regex:detect_kernel -s 3 -c 2 
     python scripts/prof_one.py extract > /dev/null 2>&1
 timeout 600 $NCU --set full --import-source on -k regex:"lowpass_kernel|scaledown_kernel|describe_kernel" -s 18 -c 6 -f -o gpurun_out/prof_pyramid \
     python scripts/prof_one.py extract > /dev/null 2>&1
-timeout 600 $NCU --set full --import-source on -k regex:"tc_" -s 6 -c 6 -f -o gpurun_out/prof_match \
+timeout 600 $NCU --set full --import-source on -k regex:"t3_" -s 3 -c 3 -f -o gpurun_out/prof_match \
     python scripts/prof_one.py match > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep

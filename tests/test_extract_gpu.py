@@ -157,3 +157,35 @@ def test_extractor_pipeline_and_u8_upload(cs):
         for f in ("xpos", "ypos", "scale", "orientation", "subsampling", "data"):
             assert np.array_equal(g[f], want[f]), f
     ex.close()
+
+
+def test_detector_variants_identical(cs):
+    """Every compiled detector configuration (CTA size, columns per horizontal task, row pairs per
+    vertical task) produces the same keypoints, bit for bit: tiling must not influence the results."""
+    arr = synth_image(1000, 700, seed=21)
+    L = cs.lib()
+    try:
+        assert L.cs_set_tuning(b"detect_variant", 0) == 0
+        base = canon(_extract(cs, arr, thresh=2.0))
+        assert len(base) > 500
+        for v in range(1, 8):
+            assert L.cs_set_tuning(b"detect_variant", v) == 0
+            got = canon(_extract(cs, arr, thresh=2.0))
+            assert len(got) == len(base), v
+            for f in ("xpos", "ypos", "scale", "sharpness", "edgeness", "orientation", "subsampling"):
+                assert np.array_equal(got[f], base[f]), (v, f)
+            assert np.array_equal(got["data"], base["data"]), v
+    finally:
+        L.cs_set_tuning(b"detect_variant", 0)
+    assert L.cs_set_tuning(b"no_such_key", 1) < 0
+
+
+def test_dense_candidates_low_threshold(cs):
+    """thresh close to 0 flags almost every pixel: the thread-per-item extrema path, the keypoint queue
+    overflow path and the maxPts clamp are all exercised; counts agree with the oracle."""
+    arr = synth_image(320, 240, seed=9)
+    got = _extract(cs, arr, thresh=0.05)
+    want, _ = oracle.extract(arr, 5, 1.0, 0.05)
+    assert len(want) > 2000
+    assert abs(len(got) - len(want)) <= 0.003 * len(want) + 2
+    _assert_close(compare_sets(canon(got), canon(want)), min_frac=0.99)
