@@ -1,8 +1,9 @@
 #!/bin/bash
-# Per-kernel durations of the single-pass matcher under the CS_TC_DBG experiments + one full capture.
+# Matcher experiments (CS_TC_DBG bits, see TcPlan::dbg): per-kernel durations under ncu, then the real
+# (warm-cache) per-kernel times from CUDA events and the bit-exact comparison against the exact path.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-for dbg in 0; do
+for dbg in ${1:-0 8}; do
   echo "== CS_TC_DBG=$dbg"
   CS_TC_DBG=$dbg timeout 120 ncu --clock-control none --csv --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
      -k regex:"t3_|match_exact" -s 8 -c 4 python scripts/prof_one.py match 2>/dev/null | grep -E '^"' | python -c "
@@ -12,9 +13,8 @@ k=h.index('Kernel Name'); m=h.index('Metric Name'); v=h.index('Metric Value')
 out={}
 for r in rows[1:]:
     out.setdefault((r[0],r[k].split('(')[0]),{})[r[m]]=r[v]
-for (i,n),d in out.items(): print('  %-22s %8s us  tensor %6s %%'%(n,d.get('gpu__time_duration.sum'),d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')))
+for (i,n),d in out.items(): print('  %-22s %8s ns  tensor %6s %%'%(n,d.get('gpu__time_duration.sum'),d.get('sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')))
 "
 done
 timeout 90 python scripts/tc_bench.py 2000 10000 2>&1 | tail -6
-timeout 300 python -m pytest tests/test_match_gpu.py -m gpu -q --timeout=200 2>&1 | tail -3
-
+CUDASIFT_MATCH_TIMING=1 timeout 90 python scripts/tc_bench.py 10000 2>&1 | grep "match timing" | tail -2
