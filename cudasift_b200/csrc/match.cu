@@ -32,15 +32,20 @@ __device__ __forceinline__ void part_update(PartState &s, float sc, int p2)
   else if (sc > s.sec) s.sec = sc;
 }
 
-// rows == nullptr: the CTA handles rows [32*blockIdx.x, +32) of set 1.  rows != nullptr: it
-// handles entries [32*b, +32) of the row list (*nrows entries), b grid-strided -- the
-// fallback of the tensor-core path for rows it could not certify.
+// rows == nullptr: the CTAs handle rows [32*b, +32) of set 1, b grid-strided.  rows != nullptr: they
+// handle entries [32*b, +32) of the row list (*nrows entries) -- the fallback of the tensor-core
+// path for rows it could not certify.
 __global__ void __launch_bounds__(MX_THREADS)
 match_exact_kernel(SiftPoint *__restrict__ sift1, const SiftPoint *__restrict__ sift2, int n1, int n2,
                    const int *__restrict__ rows, const unsigned int *__restrict__ nrows,
                    const unsigned int *__restrict__ gate)
 {
-  if (gate && *gate == 0) return;      // device-side switch: the tensor path's "inputs out of range" flag
+  // device-side switch (tensor path): *gate != 0 = the inputs were out of range for the split-FP16 screening,
+  // scan every row exactly; otherwise only the rows of the list
+  if (gate) {
+    if (*gate != 0) rows = nullptr;
+    else if (!rows) return;
+  }
   __shared__ float4 s_a[MX_ROWS * MX_LD];
   __shared__ float4 s_b[MX_COLS * MX_LD];
   const int tid = threadIdx.x;
@@ -137,20 +142,14 @@ int match_exact(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_t
   return 0;
 }
 
-// full exact scan that only runs if *gate != 0 (decided on the device, no host round trip)
-int match_exact_gated(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, const unsigned int *gate, cudaStream_t st)
+// Fallback of the tensor path in one launch, decided on the device (no host round trip): the listed
+// rows, or every row if *gate != 0.
+int match_exact_fallback(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, const int *rows, const unsigned int *nrows,
+                         const unsigned int *gate, cudaStream_t st)
 {
   if (n1 <= 0) return 0;
-  match_exact_kernel<<<idivup(n1, MX_ROWS), MX_THREADS, 0, st>>>(s1, s2, n1, n2, nullptr, nullptr, gate);
-  count_launch();
-  CS_CUDA(cudaGetLastError());
-  return 0;
-}
-
-int match_exact_rows(SiftPoint *s1, const SiftPoint *s2, int n2, const int *rows, const unsigned int *nrows,
-                     cudaStream_t st)
-{
-  match_exact_kernel<<<128, MX_THREADS, 0, st>>>(s1, s2, 0, n2, rows, nrows, nullptr);
+  const int blocks = idivup(n1, MX_ROWS) < 296 ? idivup(n1, MX_ROWS) : 296;    // grid-stride over the rows
+  match_exact_kernel<<<blocks, MX_THREADS, 0, st>>>(s1, s2, n1, n2, rows, nrows, gate);
   count_launch();
   CS_CUDA(cudaGetLastError());
   return 0;

@@ -179,10 +179,11 @@ struct T3Buffers {
 __global__ void __launch_bounds__(512)
 t3_prep_kernel(const SiftPoint *__restrict__ ptsA, int nA, __half *__restrict__ outA, float *__restrict__ norms,
                int blocksA, const SiftPoint *__restrict__ ptsB, int nB, __half *__restrict__ outB,
-               float *__restrict__ bmax)
+               float *__restrict__ bmax, float *__restrict__ nextFlags)
 {
   __shared__ float s_sq[16][33];
   __shared__ int s_bad;
+  if (blockIdx.x == 0 && threadIdx.x < 16) nextFlags[threadIdx.x] = 0.0f;   // the next call's flag area
   const int isB = (int)blockIdx.x >= blocksA;
   const SiftPoint *__restrict__ pts = isB ? ptsB : ptsA;
   const int nvalid = isB ? nB : nA;
@@ -646,9 +647,8 @@ t3_resolve_kernel(const TcPlan pl, const T3Buffers bf, SiftPoint *__restrict__ s
 }
 
 // exact SIMT scan of the rows the tensor path could not certify (match.cu)
-int match_exact_rows(SiftPoint *s1, const SiftPoint *s2, int n2, const int *rows, const unsigned int *nrows,
-                     cudaStream_t st);
-int match_exact_gated(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, const unsigned int *gate, cudaStream_t st);
+int match_exact_fallback(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, const int *rows, const unsigned int *nrows,
+                         const unsigned int *gate, cudaStream_t st);
 
 // ------------------------------------------------------------------------------ host
 static int ensure(void **p, size_t *cap, size_t bytes)
@@ -673,6 +673,8 @@ struct T3Workspace {
   T3Buffers bf = {};
   size_t cap[8] = {};
   unsigned int *h_counters = nullptr;
+  float *flags = nullptr;         // 2 x 16 words: [0] max norm of set 2, [1] bad-input flag, [4..7] counters
+  unsigned long long calls = 0;
   bool configured = false;
   bool pendingStats = false;
 };
@@ -707,12 +709,18 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
   if ((r = ensure((void **)&bf.normA, &ws.cap[2], rowsPad * sizeof(float))) < 0) return r;
   if ((r = ensure((void **)&bf.pm, &ws.cap[3], slots * T3_PM * sizeof(float))) < 0) return r;
   if ((r = ensure((void **)&bf.fbRows, &ws.cap[4], rowsPad * sizeof(int))) < 0) return r;
-  if (!bf.bmax) {
+  // flags/counters: two 64-byte areas used alternately; a call's prep kernel clears the other one for the
+  // next call, which saves a memset node per call
+  if (!ws.flags) {
     size_t dummy = 0;
-    if ((r = ensure((void **)&bf.bmax, &dummy, 64)) < 0) return r;
-    bf.counters = reinterpret_cast<unsigned int *>(bf.bmax) + 4;
+    if ((r = ensure((void **)&ws.flags, &dummy, 128)) < 0) return r;
+    CS_CUDA(cudaMemsetAsync(ws.flags, 0, 128, st));
     CS_CUDA(cudaMallocHost((void **)&ws.h_counters, 64));
   }
+  bf.bmax = ws.flags + 16 * (ws.calls & 1);
+  float *nextFlags = ws.flags + 16 * ((ws.calls + 1) & 1);
+  ws.calls++;
+  bf.counters = reinterpret_cast<unsigned int *>(bf.bmax) + 4;
   if (!ws.configured) {
     CS_CUDA(cudaFuncSetAttribute(t3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
     ws.configured = true;
@@ -726,10 +734,9 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
     if (timing) for (int i = 0; i < 6; i++) cudaEventCreate(&tev[i]);
   }
   if (timing) cudaEventRecord(tev[0], st);
-  CS_CUDA(cudaMemsetAsync(bf.bmax, 0, 64, st));
   const int blocksA = pl.n_mt * (T3_MT / 32), blocksB = pl.n_nt * (T3_N / 32);
   if (timing) cudaEventRecord(tev[1], st);
-  t3_prep_kernel<<<blocksA + blocksB, 512, 0, st>>>(s1, n1, bf.a16, bf.normA, blocksA, s2, n2v, bf.b16, bf.bmax);
+  t3_prep_kernel<<<blocksA + blocksB, 512, 0, st>>>(s1, n1, bf.a16, bf.normA, blocksA, s2, n2v, bf.b16, bf.bmax, nextFlags);
   if (timing) cudaEventRecord(tev[2], st);
   t3_gemm_kernel<<<pl.grid, T3_THREADS, T3_SMEM_BYTES, st>>>(pl, bf);
   if (timing) cudaEventRecord(tev[3], st);
@@ -737,17 +744,17 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
   if (timing) cudaEventRecord(tev[4], st);
   count_launch(3);
   CS_CUDA(cudaGetLastError());
-  if ((r = match_exact_rows(s1, s2, n2, bf.fbRows, bf.counters, st)) < 0) return r;
+  // rows that could not be certified -- or, for inputs the split cannot bound (|x| >= 8, NaN, Inf), every row --
+  // go through the exact kernel; which of the two is decided on the device
+  if ((r = match_exact_fallback(s1, n1, s2, n2, bf.fbRows, bf.counters, reinterpret_cast<const unsigned int *>(bf.bmax) + 1, st)) < 0) return r;
   if (timing) {
     cudaEventRecord(tev[5], st);
     cudaEventSynchronize(tev[5]);
     float ms[5];
     for (int i = 0; i < 5; i++) cudaEventElapsedTime(&ms[i], tev[i], tev[i + 1]);
-    fprintf(stderr, "match timing %dx%d [us]: memset %.1f prep %.1f gemm %.1f resolve %.1f exact-rows %.1f\n", n1, n2,
+    fprintf(stderr, "match timing %dx%d [us]: memset %.1f prep %.1f gemm %.1f resolve %.1f exact-fallback %.1f\n", n1, n2,
             ms[0] * 1e3f, ms[1] * 1e3f, ms[2] * 1e3f, ms[3] * 1e3f, ms[4] * 1e3f);
   }
-  // inputs the split cannot bound (|x| >= 8, NaN, Inf): redo everything exactly -- decided on the device
-  if ((r = match_exact_gated(s1, n1, s2, n2, reinterpret_cast<const unsigned int *>(bf.bmax) + 1, st)) < 0) return r;
   CS_CUDA(cudaMemcpyAsync(ws.h_counters, bf.bmax, 64, cudaMemcpyDeviceToHost, st));
   ws.pendingStats = true;               // read by match_tensor_stats() after the caller's synchronize
   return 0;

@@ -109,3 +109,41 @@ def test_match_extracted_descriptors(cs):
     # positions and descriptors belong together
     hit = (np.abs(dx - 11) < 0.5) & (np.abs(dy - 7) < 0.5)
     assert hit.mean() > 0.15, (hit.mean(), good.sum())
+
+
+def test_match_out_of_range_inputs_take_the_exact_path(cs):
+    """|x| >= 8 (or NaN/Inf) cannot be bounded by the split-FP16 screening: the device-side gate sends
+    every row through the exact kernel, no host round trip, same results as mode 1."""
+    s1, s2 = synth_descriptors(600, 11), synth_descriptors(700, 12)
+    s2["data"][5, 17] = 100.0
+    a, _ = cs.match_host(s1, s2, mode=1)
+    b, _ = cs.match_host(s1, s2, mode=2)
+    _eq(b, a, "out of range")
+    assert cs.match_stats()[2] > len(s1)            # flagged: everything went the exact way
+    s2 = synth_descriptors(700, 12)
+    s1["data"][3, 0] = np.nan
+    a, _ = cs.match_host(s1, s2, mode=1)
+    b, _ = cs.match_host(s1, s2, mode=2)
+    for f in ("score", "ambiguity", "match", "match_xpos", "match_ypos"):
+        assert a[f].tobytes() == b[f].tobytes(), f
+    # and the next call with clean inputs is back on the tensor path (the flag areas alternate)
+    s1 = synth_descriptors(600, 11)
+    a, _ = cs.match_host(s1, s2, mode=1)
+    b, _ = cs.match_host(s1, s2, mode=2)
+    _eq(b, a, "clean again")
+    assert cs.match_stats()[2] < 0.01 * len(s1)
+
+
+def test_match_triplicates_fall_back_per_row(cs):
+    """Three identical candidates in one partition (p2 = 0, 32, 64) tie the three largest group maxima of
+    every row that likes them: such rows cannot be certified and are re-scanned exactly -- same output."""
+    s1, s2 = synth_descriptors(512, 21), synth_descriptors(640, 22)
+    s2["data"][32] = s2["data"][0]
+    s2["data"][64] = s2["data"][0]
+    s1["data"][:64] = s2["data"][0] * 0.999 + s1["data"][:64] * 0.001      # rows whose best match is the triplicate
+    a, _ = cs.match_host(s1, s2, mode=1)
+    b, _ = cs.match_host(s1, s2, mode=2)
+    _eq(b, a, "triplicates")
+    st = cs.match_stats()
+    assert 0 < st[2] < len(s1)
+    assert (a["match"][:64] == 0).all()             # lowest index wins the tie (matching.cu:354, strict '>')
