@@ -371,9 +371,33 @@ def cpu_baseline(imgs):
     [t.join() for t in ths]
     dt = time.perf_counter() - t0
     n = threads * per_thread
-    return {"value": round(n / dt, 2), "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": "%d synthetic 1920x1080 images through oracle_extract (scalar C restatement), %d threads, %.1f s"
-                      % (n, threads, dt)}
+    out = {"value": round(n / dt, 2), "unit": "images/s", "cores": threads, "kind": "port",
+           "sample": "%d synthetic 1920x1080 images through oracle_extract (scalar C restatement), %d threads, %.1f s"
+                     % (n, threads, dt)}
+    out["opencv_sift"] = opencv_sift_baseline(imgs, cores)
+    return out
+
+
+def opencv_sift_baseline(imgs, cores, budget_s=6.0):
+    """BASELINE.json's "scalar CPU OpenCV-SIFT baseline on the host cores, core count stated": a different
+    algorithm variant (OpenCV's SIFT, 8-bit input), reported for orientation only; 1 thread, then all cores."""
+    try:
+        import cv2
+    except Exception as e:                                    # not part of the contract: absent -> say so
+        return {"unavailable": str(e)[:80]}
+    im8 = [np.clip(np.rint(im), 0, 255).astype(np.uint8) for im in imgs[:4]]
+    sift = cv2.SIFT_create(nOctaveLayers=5)
+    res = {"host_cores": cores, "nOctaveLayers": 5}
+    for name, nthreads in (("scalar", 1), ("all_cores", cores)):
+        cv2.setNumThreads(nthreads)
+        sift.detectAndCompute(im8[0], None)                   # warm
+        t0, k, nk = time.perf_counter(), 0, 0
+        while time.perf_counter() - t0 < budget_s / 2 and k < 64:
+            kp, _ = sift.detectAndCompute(im8[k % len(im8)], None)
+            nk += len(kp); k += 1
+        dt = time.perf_counter() - t0
+        res[name] = {"images_per_s": round(k / dt, 2), "threads": nthreads, "images": k, "features_per_image": round(nk / max(k, 1))}
+    return res
 
 
 # ------------------------------------------------------------------------------------------
