@@ -223,9 +223,7 @@ int Pipeline::enqueue(const float *d_img, int pitch, double initBlur, float thre
     if (lw[i] < 3 || lh[i] < 3) continue;          // no interior pixel -> no extrema possible
     DetectLevel &L = dp.lev[nl++];
     L.img = lev[i]; L.w = lw[i]; L.h = lh[i]; L.pitch = lp[i];
-    L.tilesX = idivup(lw[i] - 2, CS_DETECT_TILE_W); L.tilesY = idivup(lh[i] - 2, CS_DETECT_TILE_H);
-    L.tileBase = tiles;
-    tiles += L.tilesX * L.tilesY;
+    tiles += idivup(lw[i] - 2, CS_DETECT_TILE_W) * idivup(lh[i] - 2, CS_DETECT_TILE_H);   // see Pipeline::init (d_tiles)
     L.subsampling = (float)(1 << i);
     L.lowestScale = lowestScale / L.subsampling;                           // cudaSiftH.cu:213
     const float *k = lapTaps + (numOctaves - i) * 12 * 16;                 // octave index, :161,:1766

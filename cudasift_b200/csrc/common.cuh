@@ -69,8 +69,6 @@ int launch_u8_to_float(const uint8_t *src, int srcPitch, float *dst, int dstPitc
 struct DetectLevel {
   const float *img;     // octave base image
   int w, h, pitch;
-  int tilesX, tilesY;
-  int tileBase;         // first linear block id of this level
   float subsampling;
   float lowestScale;    // lowestScale / subsampling, cudaSiftH.cu:213
   LaplaceTaps taps;

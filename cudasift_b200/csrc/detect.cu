@@ -36,7 +36,6 @@ namespace cs {
 #define DT_H 16               // DoG tile height  (14 interior rows)
 #define DT_HP (DT_H / 2)      // row pairs (r, r+8)
 #define DT_IW (DT_W + 8)      // 72 staged input columns
-#define DT_IH (DT_H + 8)      // 24 staged input rows
 #define DT_PH 4               // scales blurred per phase (2 phases)
 #define DT_VS 74              // float2 stride of a vertical-result row (37 16-byte chunks: odd -> the 8 row
                               // pairs of a quarter warp hit 8 different bank groups)
