@@ -149,14 +149,15 @@ __device__ __forceinline__ size_t tc_slot(const TcPlan &pl, int cta, int run, in
 // the kernel is tensor-pipe bound (12*N cycles of MMA against 8*N cycles of TMEM reads per tile).
 #define T3_M 128                    // rows per accumulator (UMMA M)
 #define T3_MT 256                   // rows per CTA tile (two accumulators)
-#define T3_N 64                     // candidates per stage (UMMA N)
+#define T3_N 128                    // candidates per stage (UMMA N)
 #define T3_A_PART (T3_MT * 256)     // 64 KB: hi (or lo) halves of an A tile, [half][chunk][128 rows][16 B]
 #define T3_A_BYTES (2 * T3_A_PART)  // 128 KB
-#define T3_B_PART (T3_N * 256)      // 16 KB: [chunk][64 rows][16 B]
-#define T3_B_BYTES (2 * T3_B_PART)  // 32 KB
-#define T3_STAGES 3
+#define T3_B_PART (T3_N * 256)      // 32 KB: [chunk][128 rows][16 B]
+#define T3_B_BYTES (2 * T3_B_PART)  // 64 KB
+#define T3_STAGES 3                 // B stages; the A tile passes through stages 0+1 on its way to tensor memory
 #define T3_THREADS 384
-#define T3_SMEM_BYTES (T3_A_BYTES + T3_STAGES * T3_B_BYTES + 1024)
+#define T3_SMEM_BYTES (T3_STAGES * T3_B_BYTES + 1024)
+static_assert(T3_A_BYTES == 2 * T3_B_BYTES, "the A tile is staged in two B stages");
 #define T3_PM 40                    // words per (row, segment): g1[8] g2[8] g3[8] i1[8] i2[8]
 #define T3_SCALE 4096.0f            // 2^12 per operand -> scores carry 2^24
 #define T3_UNSCALE (1.0f / 16777216.0f)
@@ -254,10 +255,9 @@ t3_gemm_kernel(const TcPlan pl, const T3Buffers bf)
 {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t *sA = smem;
-  uint8_t *sB = smem + T3_A_BYTES;
+  uint8_t *sB = smem;                  // T3_STAGES x 64 KB; stages 0+1 double as the A staging area
   __shared__ uint64_t bar_a_full, bar_a_empty, bar_b_full[T3_STAGES], bar_b_empty[T3_STAGES];
-  __shared__ uint64_t bar_acc_full[4], bar_acc_empty[4];      // [half * 2 + buffer]
+  __shared__ uint64_t bar_acc_full[2], bar_acc_empty[2];      // [row half]
   __shared__ uint64_t bar_drain;
   __shared__ uint32_t s_tmem;
 
@@ -268,7 +268,7 @@ t3_gemm_kernel(const TcPlan pl, const T3Buffers bf)
   if (threadIdx.x == 0) {
     mbar_init(&bar_a_full, 1); mbar_init(&bar_a_empty, 1); mbar_init(&bar_drain, 1);
     for (int s = 0; s < T3_STAGES; s++) { mbar_init(&bar_b_full[s], 1); mbar_init(&bar_b_empty[s], 1); }
-    for (int h = 0; h < 4; h++) { mbar_init(&bar_acc_full[h], 1); mbar_init(&bar_acc_empty[h], 128); }
+    for (int h = 0; h < 2; h++) { mbar_init(&bar_acc_full[h], 1); mbar_init(&bar_acc_empty[h], 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -280,23 +280,32 @@ t3_gemm_kernel(const TcPlan pl, const T3Buffers bf)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = s_tmem;
+  // tensor memory map: columns [0,128) accumulator of rows 0..127, [128,256) of rows 128..255,
+  // [256,512) the A tile: [row half][hi|lo][8 K steps][8 columns]
 
   if (warp == 0) {
     // ============================ producer: bulk copies of whole operand tiles ============================
     if (lane == 0) {
       int runIdx = 0, prevMt = -1;
+      int uses[T3_STAGES];
+      for (int s = 0; s < T3_STAGES; s++) uses[s] = 0;
       for (int u = u_begin, i = 0; u < u_end; u++, i++) {
         const int mt = u / pl.n_nt, nt = u - mt * pl.n_nt;
         if (mt != prevMt) {
-          if (runIdx > 0) mbar_wait(&bar_a_empty, (runIdx - 1) & 1);
+          // the A tile goes through the B stages: they must all have been consumed ...
+          for (int s = 0; s < T3_STAGES; s++)
+            if (uses[s] > 0) mbar_wait(&bar_b_empty[s], (uses[s] - 1) & 1);
           mbar_expect_tx(&bar_a_full, T3_A_BYTES);
           const uint8_t *srcA = reinterpret_cast<const uint8_t *>(bf.a16) + (size_t)mt * T3_A_BYTES;
-          bulk_g2s(sA, srcA, T3_A_PART, &bar_a_full);
-          bulk_g2s(sA + T3_A_PART, srcA + T3_A_PART, T3_A_PART, &bar_a_full);
+          bulk_g2s(sB, srcA, T3_A_PART, &bar_a_full);
+          bulk_g2s(sB + T3_A_PART, srcA + T3_A_PART, T3_A_PART, &bar_a_full);
+          // ... and are free again once the MMA warp has copied the tile into tensor memory
+          mbar_wait(&bar_a_empty, runIdx & 1);
           prevMt = mt; runIdx++;
         }
         const int s = i % T3_STAGES, it = i / T3_STAGES;
         if (it > 0) mbar_wait(&bar_b_empty[s], (it - 1) & 1);
+        uses[s] = it + 1;
         if ((pl.dbg & 1) && it > 0) { mbar_arrive(&bar_b_full[s]); continue; }   // experiment: no B traffic
         mbar_expect_tx(&bar_b_full[s], T3_B_BYTES);
         bulk_g2s(sB + s * T3_B_BYTES, reinterpret_cast<const uint8_t *>(bf.b16) + (size_t)nt * T3_B_BYTES, T3_B_BYTES, &bar_b_full[s]);
@@ -305,92 +314,61 @@ t3_gemm_kernel(const TcPlan pl, const T3Buffers bf)
   } else if (warp == 1) {
     // ============================ MMA issuer ============================
     // The whole warp walks the loop (uniform control flow, so descriptors live in uniform registers and
-    // an MMA costs a handful of instructions: the budget is 32 cycles per M128 N64 K16 instruction);
-    // one elected lane issues the tcgen05 instructions.
+    // an MMA costs a handful of instructions); one elected lane issues the tcgen05 instructions.
     {
       int runIdx = 0, prevMt = -1;
-      const bool ss = (pl.dbg & 8) != 0;          // experiment (bit 3): A operand from shared memory
-      const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB);
+      const uint32_t bBase = smem_u32(sB);
       for (int u = u_begin, i = 0; u < u_end; u++, i++) {
         const int mt = u / pl.n_nt;
         if (mt != prevMt) {
           mbar_wait(&bar_a_full, runIdx & 1);
           tc_fence_after();
-          if (!ss) {
-            // A tile -> tensor memory columns [256, 512): [half][hi|lo][8 K steps][8 columns].  The MMAs of the
-            // previous tile must have drained before their operand is overwritten.
-            if (runIdx > 0) {
-              if (elect_one()) tc_commit(&bar_drain);
-              __syncwarp();
-              mbar_wait(&bar_drain, (runIdx - 1) & 1);
-              tc_fence_after();
-            }
-            if (elect_one()) {
-#pragma unroll 1
-              for (int e = 0; e < 32; e++) {          // e = (half, part, K step)
-                const int hh = e >> 4, part = (e >> 3) & 1, k = e & 7;
-                const uint64_t sd = umma_desc(aBase + part * T3_A_PART + (uint32_t)(hh * TC_KCH + 2 * k) * (T3_M * 16), T3_M * 16, 128);
-                tc_cp_128x256b(tmem + 256 + hh * 128 + part * 64 + k * 8, sd);
-              }
-              tc_commit(&bar_a_empty);              // shared-memory A is free as soon as the copies are done
-            }
+          // A tile -> tensor memory.  The MMAs of the previous tile must have drained before their operand is
+          // overwritten.
+          if (runIdx > 0) {
+            if (elect_one()) tc_commit(&bar_drain);
             __syncwarp();
+            mbar_wait(&bar_drain, (runIdx - 1) & 1);
+            tc_fence_after();
           }
+          if (elect_one()) {
+#pragma unroll 1
+            for (int e = 0; e < 32; e++) {          // e = (half, part, K step)
+              const int hh = e >> 4, part = (e >> 3) & 1, k = e & 7;
+              const uint64_t sd = umma_desc(bBase + part * T3_A_PART + (uint32_t)(hh * TC_KCH + 2 * k) * (T3_M * 16), T3_M * 16, 128);
+              tc_cp_128x256b(tmem + 256 + hh * 128 + part * 64 + k * 8, sd);
+            }
+            tc_commit(&bar_a_empty);                // the staging area is free as soon as the copies are done
+          }
+          __syncwarp();
           prevMt = mt; runIdx++;
         }
         const int s = i % T3_STAGES, it = i / T3_STAGES;
         mbar_wait(&bar_b_full[s], it & 1);
-        const int buf = i & 1, k2 = i >> 1;
-        mbar_wait(&bar_acc_empty[0 * 2 + buf], (k2 & 1) ^ 1);      // first use passes on a fresh barrier
-        mbar_wait(&bar_acc_empty[1 * 2 + buf], (k2 & 1) ^ 1);
-        tc_fence_after();
-        {
-          // K=16 step k = chunks 2k, 2k+1.  A part: [half][chunk][128 rows][16 B]; B part: [chunk][64 rows][16 B].
-          // The two row halves alternate so that consecutive MMAs never accumulate into the same TMEM columns.
-          const uint32_t d0 = tmem + (uint32_t)((0 * 2 + buf) * T3_N), d1 = tmem + (uint32_t)((1 * 2 + buf) * T3_N);
-          const uint64_t a0 = umma_desc(aBase, T3_M * 16, 128);
-          const uint64_t a1 = umma_desc(aBase + (uint32_t)TC_KCH * (T3_M * 16), T3_M * 16, 128);
-          const uint64_t bhi0 = umma_desc(bBase + s * T3_B_BYTES, T3_N * 16, 128);
-          if (!ss) {
-            if (elect_one()) {
-              const uint32_t ta0 = tmem + 256, ta1 = tmem + 256 + 128;     // hi at +0, lo at +64, K step k at +8k
+        const uint64_t bhi0 = umma_desc(bBase + s * T3_B_BYTES, T3_N * 16, 128);
 #pragma unroll
-              for (int k = 0; k < 8; k++) {
-                const uint64_t kb = (uint64_t)((2 * k * (T3_N * 16)) >> 4);
-                const uint64_t bhi = bhi0 + kb, blo = bhi + (uint64_t)(T3_B_PART >> 4);
-                tc_mma_f16_ts(d0, ta0 + 8 * k, bhi, T3_IDESC, k > 0 ? 1u : 0u);
-                tc_mma_f16_ts(d1, ta1 + 8 * k, bhi, T3_IDESC, k > 0 ? 1u : 0u);
-                tc_mma_f16_ts(d0, ta0 + 8 * k, blo, T3_IDESC, 1u);
-                tc_mma_f16_ts(d1, ta1 + 8 * k, blo, T3_IDESC, 1u);
-                tc_mma_f16_ts(d0, ta0 + 64 + 8 * k, bhi, T3_IDESC, 1u);
-                tc_mma_f16_ts(d1, ta1 + 64 + 8 * k, bhi, T3_IDESC, 1u);
-              }
-              tc_commit(&bar_acc_full[0 * 2 + buf]);
-              tc_commit(&bar_acc_full[1 * 2 + buf]);
-            }
-          } else if (elect_one()) {
+        for (int h = 0; h < 2; h++) {
+          // single-buffered accumulators: the epilogue of half h reads while the MMAs of the other half run
+          mbar_wait(&bar_acc_empty[h], (i & 1) ^ 1);              // first use passes on a fresh barrier
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t d = tmem + (uint32_t)(h * T3_N);
+            const uint32_t ta = tmem + 256 + h * 128;             // hi at +0, lo at +64, K step k at +8k
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-              // advancing the 14-bit start-address field (units of 16 bytes) moves the operand window
-              const uint64_t ka = (uint64_t)((2 * k * (T3_M * 16)) >> 4), kb = (uint64_t)((2 * k * (T3_N * 16)) >> 4);
+              // K=16 step k = chunks 2k, 2k+1 of the B part [chunk][128 rows][16 B]; advancing the 14-bit
+              // start-address field (units of 16 bytes) moves the operand window
+              const uint64_t kb = (uint64_t)((2 * k * (T3_N * 16)) >> 4);
               const uint64_t bhi = bhi0 + kb, blo = bhi + (uint64_t)(T3_B_PART >> 4);
-              tc_mma_f16(d0, a0 + ka, bhi, T3_IDESC, k > 0 ? 1u : 0u);
-              tc_mma_f16(d1, a1 + ka, bhi, T3_IDESC, k > 0 ? 1u : 0u);
-              tc_mma_f16(d0, a0 + ka, blo, T3_IDESC, 1u);
-              tc_mma_f16(d1, a1 + ka, blo, T3_IDESC, 1u);
-              tc_mma_f16(d0, a0 + ka + (uint64_t)(T3_A_PART >> 4), bhi, T3_IDESC, 1u);
-              tc_mma_f16(d1, a1 + ka + (uint64_t)(T3_A_PART >> 4), bhi, T3_IDESC, 1u);
+              tc_mma_f16_ts(d, ta + 8 * k, bhi, T3_IDESC, k > 0 ? 1u : 0u);
+              tc_mma_f16_ts(d, ta + 8 * k, blo, T3_IDESC, 1u);
+              tc_mma_f16_ts(d, ta + 64 + 8 * k, bhi, T3_IDESC, 1u);
             }
-            tc_commit(&bar_acc_full[0 * 2 + buf]);
-            tc_commit(&bar_acc_full[1 * 2 + buf]);
+            tc_commit(&bar_acc_full[h]);
           }
           __syncwarp();
         }
-        const bool lastOfRun = (u + 1 == u_end) || ((u + 1) / pl.n_nt != mt);
-        if (elect_one()) {
-          tc_commit(&bar_b_empty[s]);
-          if (lastOfRun && ss) tc_commit(&bar_a_empty);
-        }
+        if (elect_one()) tc_commit(&bar_b_empty[s]);
         __syncwarp();
       }
     }
@@ -416,6 +394,7 @@ t3_gemm_kernel(const TcPlan pl, const T3Buffers bf)
         g1[j] = fmaxf(g1[j], v);
       }
     };
+    const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(h * T3_N);
     for (int u = u_begin, i = 0; u < u_end; u++, i++) {
       const int mt = u / pl.n_nt, nt = u - mt * pl.n_nt;
       if (mt != prevMt) {
@@ -424,25 +403,29 @@ t3_gemm_kernel(const TcPlan pl, const T3Buffers bf)
 #pragma unroll
         for (int p = 0; p < 8; p++) { g1[p] = 0.0f; g2[p] = 0.0f; g3[p] = 0.0f; i1[p] = -1; i2[p] = -1; }
       }
-      const int buf = i & 1, k2 = i >> 1;
-      const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((h * 2 + buf) * T3_N);
-      mbar_wait(&bar_acc_full[h * 2 + buf], k2 & 1);
+      mbar_wait(&bar_acc_full[h], i & 1);
       tc_fence_after();
-      uint32_t ra[32], rb[32];
+      uint32_t ra[32], rb[32], rc[32], rd[32];
       if (!(pl.dbg & 4)) {                           // experiment (bit 2): no TMEM reads at all
         tc_ld32_issue(tbase, ra);
         tc_ld32_issue(tbase + 32, rb);
+        tc_ld32_issue(tbase + 64, rc);
+        tc_ld32_issue(tbase + 96, rd);
         tc_ld_wait(ra);
         tc_ld_wait(rb);
+        tc_ld_wait(rc);
+        tc_ld_wait(rd);
       } else {
 #pragma unroll
-        for (int e = 0; e < 32; e++) { ra[e] = 0; rb[e] = 0; }
+        for (int e = 0; e < 32; e++) { ra[e] = 0; rb[e] = 0; rc[e] = 0; rd[e] = 0; }
       }
       tc_fence_before();
-      mbar_arrive(&bar_acc_empty[h * 2 + buf]);      // the accumulator is in registers: hand it back early
+      mbar_arrive(&bar_acc_empty[h]);                // the accumulator is in registers: hand it back early
       if (!(pl.dbg & 2)) {                           // experiment (bit 1): TMEM reads without the top-3 update
         process(ra, nt * (T3_N / 4));
         process(rb, nt * (T3_N / 4) + 8);
+        process(rc, nt * (T3_N / 4) + 16);
+        process(rd, nt * (T3_N / 4) + 24);
       }
       const bool lastOfRun = (u + 1 == u_end) || ((u + 1) / pl.n_nt != mt);
       if (lastOfRun) {
