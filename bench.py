@@ -344,13 +344,13 @@ def bench_match(cs, args):
     tpeak = float(pk.get("bf16_tflops", 0.0)) or 1693.0
     t = res["tensor"]
     res["tensor_roofline"] = {
-        "bound": "tensor", "kernel": "t3_gemm_kernel (tcgen05.mma kind::f16, M128 N64 K16, A in TMEM, K_eff = 384)",
+        "bound": "tensor", "kernel": "t3_gemm_kernel (tcgen05.mma kind::f16, M128 N128 K16, A in TMEM, K_eff = 384)",
         "achieved_algorithmic": t["tflops_algorithmic"], "achieved_executed": round(3 * t["tflops_algorithmic"], 2),
         "peak": tpeak, "unit": "TFLOP/s", "frac_algorithmic": round(t["tflops_algorithmic"] / tpeak, 4),
         "frac_executed": round(3 * t["tflops_algorithmic"] / tpeak, 4),
         "peak_source": "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if pk else "fallback",
         "note": "whole MatchSiftData call (prep + GEMM + resolve + D2H of 5 fields); the GEMM kernel alone keeps the tensor "
-                "pipe active ~57 % of its cycles (profiles/, sm__pipe_tensor_cycles_active)"}
+                "pipe active 73 % of its cycles (profiles/r01_prof_match.txt, sm__pipe_tensor_cycles_active)"}
     return res
 
 

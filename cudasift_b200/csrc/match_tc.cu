@@ -11,8 +11,8 @@
 //                directly in the UMMA "interleaved" (no-swizzle, K-major) core-matrix layout so that an
 //                operand tile is one contiguous blob = one cp.async.bulk; row norms for the error bound.
 //   2. gemm      persistent warp-specialised kernel: cp.async.bulk producer warp, one elected MMA lane
-//                (tcgen05.mma kind::f16, M=128 N=64 K=16, A operand in tensor memory, three MMAs per K step:
-//                hi*hi + hi*lo + lo*hi, FP32 accumulators in TMEM, double buffered), 8 epilogue warps read
+//                (tcgen05.mma kind::f16, M=128 N=128 K=16, A operand in tensor memory, three MMAs per K step:
+//                hi*hi + hi*lo + lo*hi, FP32 accumulators in TMEM), 8 epilogue warps read
 //                the accumulators with tcgen05.ld and keep, per (row, partition), the three largest
 //                4-candidate group maxima.
 //   3. resolve   eight lanes per row: merge the segments, certify, exact k=0..127 FMA chains for the
@@ -126,7 +126,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint
 struct TcPlan {
   int n1, n2v, n_mt, n_nt, total, U, runs, grid;
   // experiments (env CS_TC_DBG, results are wrong when set): 1 = B tiles are not reloaded, 2 = TMEM reads without
-  // the top-3 update, 4 = no TMEM reads, 8 = A operand from shared memory instead of tensor memory
+  // the top-3 update, 4 = no TMEM reads
   int dbg;
 };
 // slot of (cta, run, row-in-tile)

@@ -3,7 +3,7 @@
 # (warm-cache) per-kernel times from CUDA events and the bit-exact comparison against the exact path.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-for dbg in ${1:-0 8}; do
+for dbg in ${1:-0}; do
   echo "== CS_TC_DBG=$dbg"
   CS_TC_DBG=$dbg timeout 120 ncu --clock-control none --csv --metrics gpu__time_duration.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active \
      -k regex:"t3_|match_exact" -s 8 -c 4 python scripts/prof_one.py match 2>/dev/null | grep -E '^"' | python -c "
