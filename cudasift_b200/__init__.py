@@ -13,7 +13,7 @@ import numpy as np
 
 from . import build as _build
 
-__all__ = ["SIFT_DTYPE", "lib", "InitCuda", "CudaImage", "SiftData", "InitSiftData", "FreeSiftData",
+__all__ = ["SIFT_DTYPE", "lib", "set_tuning", "InitCuda", "CudaImage", "SiftData", "InitSiftData", "FreeSiftData",
            "AllocSiftTempMemory", "FreeSiftTempMemory", "ExtractSift", "MatchSiftData", "FindHomography", "Extractor",
            "CudaSiftError", "extract_host", "match_host"]
 
@@ -86,6 +86,17 @@ def lib():
         "cs_event_record": (ip, [vp, vp]),
         "cs_event_elapsed_ms": (c.c_double, [vp, vp]),
         "cs_extractor_profile": (ip, [vp, vp, ip, c.c_double, fp, fp, c.POINTER(c.c_float)]),
+        "cs_max_batch": (ip, []),
+        "cs_extractor_create_batch": (vp, [ip, ip, ip, ip, ip, ip]),
+        "cs_extractor_submit_device_batch": (ip, [vp, ip, vp, ip, c.c_double, fp, fp]),
+        "cs_extractor_submit_host_batch": (ip, [vp, ip, vp, c.c_double, fp, fp]),
+        "cs_extractor_wait_batch": (ip, [vp, vp]),
+        "cs_extractor_count": (ip, [vp, ip]),
+        "cs_extractor_device_points_at": (vp, [vp, ip]),
+        "cs_extractor_host_points_at": (vp, [vp, ip]),
+        "cs_extractor_host_image_at": (vp, [vp, ip]),
+        "cs_extractor_profile_batch": (ip, [vp, ip, vp, ip, c.c_double, fp, fp, c.POINTER(c.c_float)]),
+        "cs_extractor_read_level": (ip, [vp, ip, ip, vp]),
         "cs_extractor_device_points": (vp, [vp]),
         "cs_extractor_host_points": (vp, [vp]),
         "cs_extractor_host_image": (vp, [vp]),
@@ -287,13 +298,60 @@ def match_host(s1, s2, mode=0):
     return s1, ms.value
 
 
-class Extractor:
-    """Pipelined extractor (one CUDA stream + arena + result buffers); see cudasift_b200.h."""
+def set_tuning(key, value):
+    return _check(lib().cs_set_tuning(key.encode(), int(value)), "cs_set_tuning")
 
-    def __init__(self, width, height, numOctaves=5, maxPts=32768, scaleUp=False):
-        self.w, self.h, self.maxPts = width, height, maxPts
-        self.handle = _check(lib().cs_extractor_create(width, height, numOctaves, maxPts, int(scaleUp)),
-                             "cs_extractor_create")
+
+class Extractor:
+    """Pipelined extractor (one CUDA stream + arena + result buffers for up to `batch` images per submit);
+    see cudasift_b200.h."""
+
+    def __init__(self, width, height, numOctaves=5, maxPts=32768, scaleUp=False, batch=1):
+        self.w, self.h, self.maxPts, self.batch = width, height, maxPts, batch
+        self.handle = _check(lib().cs_extractor_create_batch(width, height, numOctaves, maxPts, int(scaleUp), batch),
+                             "cs_extractor_create_batch")
+
+    # ---- batches: one launch per stage for n images ----
+    def submit_device_batch(self, d_imgs, pitch, initBlur=1.0, thresh=3.0, lowestScale=0.0):
+        arr = (ctypes.c_void_p * len(d_imgs))(*d_imgs)
+        _check(lib().cs_extractor_submit_device_batch(self.handle, len(d_imgs), arr, pitch, initBlur, thresh, lowestScale),
+               "submit_device_batch")
+
+    def submit_host_batch(self, h_img_ptrs, initBlur=1.0, thresh=3.0, lowestScale=0.0):
+        arr = (ctypes.c_void_p * len(h_img_ptrs))(*h_img_ptrs)
+        _check(lib().cs_extractor_submit_host_batch(self.handle, len(h_img_ptrs), arr, initBlur, thresh, lowestScale),
+               "submit_host_batch")
+
+    def wait_batch(self, n):
+        counts = (ctypes.c_int * n)()
+        _check(lib().cs_extractor_wait_batch(self.handle, counts), "wait_batch")
+        return list(counts)
+
+    def profile_batch(self, d_imgs, pitch, initBlur=1.0, thresh=3.0, lowestScale=0.0):
+        arr = (ctypes.c_void_p * len(d_imgs))(*d_imgs)
+        out = (ctypes.c_float * 5)()
+        n = _check(lib().cs_extractor_profile_batch(self.handle, len(d_imgs), arr, pitch, initBlur, thresh, lowestScale, out),
+                   "profile_batch")
+        return n, list(out)
+
+    def host_points_at(self, slot, n):
+        p = lib().cs_extractor_host_points_at(self.handle, slot)
+        buf = (ctypes.c_char * (n * SIFT_DTYPE.itemsize)).from_address(p)
+        return np.frombuffer(buf, dtype=SIFT_DTYPE, count=n)
+
+    def device_points_at(self, slot, n):
+        """Copy of the first n records of image slot `slot` (device -> host)."""
+        out = np.empty(n, SIFT_DTYPE)
+        if n:
+            _check(lib().cs_memcpy_d2h(_ptr(out), lib().cs_extractor_device_points_at(self.handle, slot), out.nbytes), "d2h")
+        return out
+
+    def read_level(self, slot, level):
+        wh = _check(lib().cs_extractor_read_level(self.handle, slot, level, None), "read_level")
+        w, h = wh & 0xffff, wh >> 16
+        out = np.empty((h, w), np.float32)
+        _check(lib().cs_extractor_read_level(self.handle, slot, level, _ptr(out)), "read_level")
+        return out
 
     def host_image(self):
         p = lib().cs_extractor_host_image(self.handle)

@@ -22,7 +22,8 @@ REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 REF_LIB = os.path.join(REF_DIR, "libcudasift_ref.so")
 REFERENCE_SRC = "/root/reference"
 
-SOURCES = ["api.cu", "pyramid.cu", "detect.cu", "describe.cu", "match.cu", "match_tc.cu", "homography.cu", "geom.cu"]
+SOURCES = ["api.cu", "pipeline2.cu", "pyramid.cu", "pyramid2.cu", "detect.cu", "detect2.cu", "cap32.cu", "describe.cu",
+           "match.cu", "match_tc.cu", "homography.cu", "geom.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-O2,-Wall", "-shared"]
 
@@ -51,7 +52,7 @@ def nvcc_path():
 
 def build_library(force=False, verbose=False):
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, "common.cuh")] + [
+    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "tma.cuh", "pipeline2.h")] + [
         os.path.join(ROOT, "include", h) for h in ("cudaSift.h", "cudaImage.h", "cudasift_b200.h")]
     if not force and _newer(LIB, deps):
         return LIB

@@ -9,6 +9,7 @@
 // per-device state instead of function-local statics (quirk Q12); quiet unless
 // CUDASIFT_VERBOSE is set (quirk Q13).
 #include "common.cuh"
+#include "pipeline2.h"
 
 #include <cmath>
 #include <cstdarg>
@@ -31,6 +32,15 @@ void set_error(const char *fmt, ...)
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+// CUDASIFT_LEGACY=1 (or cs_set_tuning("legacy", 1)): the round-1 per-image kernels instead of the batched
+// TMA pipeline.  The legacy path is also what an image that TMA cannot address (odd pitch, unaligned base) takes.
+int g_legacy = -1;
+static bool legacy_mode()
+{
+  if (g_legacy < 0) { const char *e = getenv("CUDASIFT_LEGACY"); g_legacy = (e && *e && *e != '0') ? 1 : 0; }
+  return g_legacy == 1;
 }
 
 static bool verbose()
@@ -272,7 +282,8 @@ struct PipeKey {
 struct DeviceCtx {
   int dev = -1;
   cudaStream_t stream = nullptr;           // blocking stream: ordered after legacy default-stream work
-  std::map<PipeKey, Pipeline *> pipes;
+  std::map<PipeKey, Pipeline *> pipes;     // legacy per-image pipelines
+  std::map<PipeKey, Pipeline2 *> pipes2;   // batched pipeline, batch of one (the drop-in ExtractSift)
   unsigned int *h_counters = nullptr;      // pinned
   unsigned long long matchStats[4] = {0, 0, 0, 0};
   // scratch for *_host entry points
@@ -310,11 +321,28 @@ struct DeviceCtx {
     pipes[k] = p;
     return p;
   }
+  Pipeline2 *get_pipe2(int w, int h, int oct, bool up, float *arena, int *err)
+  {
+    PipeKey k{w, h, oct, up ? 1 : 0, arena};
+    auto it = pipes2.find(k);
+    if (it != pipes2.end()) return it->second;
+    if (!arena && pipes2.size() > 8) drop_pipes(nullptr, true);
+    Pipeline2 *p = new Pipeline2();
+    int r = p->init(w, h, oct, up, 1, arena);
+    if (r < 0) { p->destroy(); delete p; *err = r; return nullptr; }
+    pipes2[k] = p;
+    return p;
+  }
   void drop_pipes(float *arena, bool internalOnly)
   {
     for (auto it = pipes.begin(); it != pipes.end();) {
       bool hit = internalOnly ? it->second->ownArena : (it->first.arena == arena);
       if (hit) { it->second->destroy(); delete it->second; it = pipes.erase(it); }
+      else ++it;
+    }
+    for (auto it = pipes2.begin(); it != pipes2.end();) {
+      bool hit = internalOnly ? it->second->ownArena : (it->first.arena == arena);
+      if (hit) { it->second->destroy(); delete it->second; it = pipes2.erase(it); }
       else ++it;
     }
   }
@@ -350,14 +378,21 @@ static int extract_sync(const float *d_img, int w, int h, int pitch, int numOcta
   if (!d_img || !d_pts || maxPts < 1) { set_error("ExtractSift: missing image or SiftData"); return CS_E_ARG; }
   DeviceCtx *c = current_ctx(&err);
   if (!c) return err;
-  Pipeline *p = c->get_pipe(w, h, numOctaves, scaleUp, d_tmp, &err);
-  if (!p) return err;
+  const bool useLegacy = legacy_mode() || !tensor_map_compatible(d_img, pitch) ||
+                         (d_tmp && (reinterpret_cast<uintptr_t>(d_tmp) & 15) != 0);
+  Pipeline *p = nullptr;
+  Pipeline2 *p2 = nullptr;
+  if (useLegacy) p = c->get_pipe(w, h, numOctaves, scaleUp, d_tmp, &err);
+  else p2 = c->get_pipe2(w, h, numOctaves, scaleUp, d_tmp, &err);
+  if (!p && !p2) return err;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (msKernel) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
-  int r = p->enqueue(d_img, pitch, initBlur, thresh, lowestScale, d_pts, maxPts, c->stream);
-  if (r < 0) return r;
+  int r = p ? p->enqueue(d_img, pitch, initBlur, thresh, lowestScale, d_pts, maxPts, c->stream)
+            : p2->enqueue(1, &d_img, pitch, initBlur, thresh, lowestScale, d_pts, 0, maxPts, c->stream);
+  if (r < 0) { if (msKernel) { cudaEventDestroy(e0); cudaEventDestroy(e1); } return r; }
   if (msKernel) cudaEventRecord(e1, c->stream);
-  CS_CUDA(cudaMemcpyAsync(c->h_counters, p->d_counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  const unsigned int *d_cnt = p ? p->d_counters : p2->counters(0);
+  CS_CUDA(cudaMemcpyAsync(c->h_counters, d_cnt, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
   CS_CUDA(cudaStreamSynchronize(c->stream));
   int numPts = count_from_counters(c->h_counters, maxPts);                 // cudaSiftH.cu:115-116
   if (msKernel) {
@@ -691,13 +726,21 @@ int cs_set_tuning(const char *key, int value)
 {
   if (key && strcmp(key, "detect_variant") == 0) { cs::g_detect_variant = value; return 0; }
   if (key && strcmp(key, "detect_skip") == 0) { cs::g_detect_skip = value; return 0; }
+  if (key && strcmp(key, "legacy") == 0) { cs::g_legacy = value ? 1 : 0; return 0; }
+  if (key && strcmp(key, "d2_hs") == 0) { cs::g_d2_hs = value; return 0; }
+  if (key && strcmp(key, "pa_rows") == 0) { cs::g_pa_rows = value; return 0; }
+  if (key && strcmp(key, "cap32") == 0) { cs::g_cap32 = value ? 1 : 0; return 0; }
   cs::set_error("cs_set_tuning: unknown key");
   return CS_E_ARG;
 }
 
 int cs_extract_launches_per_image(int numOctaves, int scaleUp)
-{ // lowpass + (numOctaves-1) scaledown + detect + describe (+ scaleup + rescale)
-  return 1 + (numOctaves - 1) + 1 + 1 + (scaleUp ? 2 : 0);
+{
+  if (legacy_mode())   // lowpass + (numOctaves-1) scaledown + detect + describe (+ scaleup + rescale)
+    return 1 + (numOctaves - 1) + 1 + 1 + (scaleUp ? 2 : 0);
+  // level-0/1 kernel + ScaleDown chain (3 levels per launch) + detect + cap fix-up + describe (+ scaleup + rescale);
+  // a batch of n images costs the same number of launches
+  return 1 + (numOctaves > 2 ? (numOctaves - 2 + 2) / 3 : 0) + 1 + (cs::g_cap32 == 0 ? 0 : 1) + 1 + (scaleUp ? 2 : 0);
 }
 
 int cs_init(int device)
@@ -895,82 +938,123 @@ int cs_tex_probe(const float *d_img, int w, int h, int pitch, const float *d_xs,
 
 // ---- pipelined extractor ----
 struct cs_extractor {
-  int w, h, numOctaves, maxPts, scaleUp, pitch;
+  int w, h, numOctaves, maxPts, scaleUp, pitch, B;
   cudaStream_t stream;
-  Pipeline pipe;
-  float *d_img;
-  SiftPoint *d_pts;
-  float *h_img;          // pinned
+  bool legacy;
+  Pipeline pipe;         // legacy per-image kernels (B == 1)
+  Pipeline2 pipe2;       // batched TMA pipeline
+  float *d_img;          // B staging images
+  SiftPoint *d_pts;      // B x maxPts records
+  float *h_img;          // pinned, B x w x h
   uint8_t *d_u8;         // device staging for 8-bit uploads (lazily allocated)
-  SiftPoint *h_pts;      // pinned
-  unsigned int *h_counters;
+  SiftPoint *h_pts;      // pinned, B x maxPts
+  unsigned int *h_counters;   // pinned, B x CS_CNT_STRIDE
   bool hostResults;
-  int lastCount;
-  // CUDA graph of one steady-state submit (memset + 7 kernels + count D2H); only the source
-  // pointer of the first kernel changes from image to image (patched with SetParams).
+  int lastN;
+  int lastCounts[CS_MAX_BATCH];
+  // CUDA graph of one steady-state submit (memset + kernels + count D2H).  Per image only the input pointer
+  // changes: legacy = first parameter of the LowPass node, batched = the tensor maps in the parameters of the
+  // first pyramid kernel; both are patched with cudaGraphExecKernelNodeSetParams.
   cudaGraphExec_t gexec;
   cudaGraph_t graph;
-  cudaGraphNode_t gnode;          // the LowPass kernel node
+  cudaGraphNode_t gnode;
   cudaKernelNodeParams gparams;
   void *gargs[16];
   const float *gsrc;
-  int gpitch;
+  PyrAParams gpa;
+  int gn, gpitch, glaunches;
   double gblur;
   float gthresh, glowest;
   int submits;
 };
 
-// Capture one submit into a graph.  Returns 0 and leaves ex->gexec == NULL if anything is
-// unsupported; the caller then launches directly.
-static int extractor_capture(cs_extractor *ex, const float *d_img, int pitch, double initBlur, float thresh,
+
+static void extractor_drop_graph(cs_extractor *ex)
+{
+  if (ex->gexec) cudaGraphExecDestroy(ex->gexec);
+  if (ex->graph) cudaGraphDestroy(ex->graph);
+  ex->gexec = nullptr; ex->graph = nullptr;
+}
+
+static int extractor_enqueue(cs_extractor *ex, int n, const float *const *d_imgs, int pitch, double initBlur, float thresh,
+                             float lowestScale, cudaEvent_t *ev, PyrAParams *paOut)
+{
+  int r;
+  if (ex->legacy) {
+    r = ex->pipe.enqueue(d_imgs[0], pitch, initBlur, thresh, lowestScale, ex->d_pts, ex->maxPts, ex->stream, ev);
+    if (r < 0) return r;
+    CS_CUDA(cudaMemcpyAsync(ex->h_counters, ex->pipe.d_counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ex->stream));
+  } else {
+    r = ex->pipe2.enqueue(n, d_imgs, pitch, initBlur, thresh, lowestScale, ex->d_pts, ex->maxPts, ex->maxPts, ex->stream, ev, paOut);
+    if (r < 0) return r;
+    CS_CUDA(cudaMemcpyAsync(ex->h_counters, ex->pipe2.d_state, (size_t)n * CS_CNT_STRIDE * sizeof(unsigned int),
+                            cudaMemcpyDeviceToHost, ex->stream));
+  }
+  return 0;
+}
+
+// Capture one submit into a graph.  Leaves ex->gexec == NULL if anything is unsupported; the caller then
+// launches directly.
+static int extractor_capture(cs_extractor *ex, int n, const float *const *d_imgs, int pitch, double initBlur, float thresh,
                              float lowestScale)
 {
   if (ex->scaleUp) return 0;
   if (getenv("CUDASIFT_NO_GRAPH")) return 0;
   cudaGraph_t g = nullptr;
   if (cudaStreamBeginCapture(ex->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return 0; }
-  int r = ex->pipe.enqueue(d_img, pitch, initBlur, thresh, lowestScale, ex->d_pts, ex->maxPts, ex->stream);
-  cudaError_t e1 = cudaMemcpyAsync(ex->h_counters, ex->pipe.d_counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ex->stream);
+  const unsigned long long l0 = cs::g_launches;
+  int r = extractor_enqueue(ex, n, d_imgs, pitch, initBlur, thresh, lowestScale, nullptr, &ex->gpa);
+  ex->glaunches = (int)(cs::g_launches - l0);
+  cs::g_launches = l0;                                   // captured, not launched
   cudaError_t e2 = cudaStreamEndCapture(ex->stream, &g);
-  if (r < 0 || e1 != cudaSuccess || e2 != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return 0; }
-  // find the kernel node that reads d_img (first kernel parameter == d_img)
-  size_t n = 0;
-  cudaGraphGetNodes(g, nullptr, &n);
-  std::vector<cudaGraphNode_t> nodes(n);
-  cudaGraphGetNodes(g, nodes.data(), &n);
+  if (r < 0 || e2 != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return 0; }
+  size_t nn = 0;
+  cudaGraphGetNodes(g, nullptr, &nn);
+  std::vector<cudaGraphNode_t> nodes(nn);
+  cudaGraphGetNodes(g, nodes.data(), &nn);
   bool found = false;
-  for (size_t i = 0; i < n && !found; i++) {
+  for (size_t i = 0; i < nn && !found; i++) {
     cudaGraphNodeType t;
     if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
     cudaKernelNodeParams kp;
     if (cudaGraphKernelNodeGetParams(nodes[i], &kp) != cudaSuccess || !kp.kernelParams) continue;
-    if (*reinterpret_cast<const float *const *>(kp.kernelParams[0]) == d_img && kp.blockDim.x == 256) {
+    if (ex->legacy) {   // the kernel node that reads d_img (first kernel parameter == d_img): lowpass_kernel, 7 parameters
+      if (*reinterpret_cast<const float *const *>(kp.kernelParams[0]) == d_imgs[0] && kp.blockDim.x == 256) {
+        ex->gnode = nodes[i]; ex->gparams = kp;
+        for (int a = 0; a < 7; a++) ex->gargs[a] = kp.kernelParams[a];
+        found = true;
+      }
+    } else if (kp.func == cs::pyr_a_func()) {
       ex->gnode = nodes[i]; ex->gparams = kp;
-      for (int a = 0; a < 7; a++) ex->gargs[a] = kp.kernelParams[a];   // lowpass_kernel has 7 parameters
       found = true;
     }
   }
   cudaGraphExec_t ge = nullptr;
   if (!found || cudaGraphInstantiate(&ge, g, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(g); return 0; }
   ex->graph = g; ex->gexec = ge;
-  ex->gsrc = d_img; ex->gpitch = pitch; ex->gblur = initBlur; ex->gthresh = thresh; ex->glowest = lowestScale;
+  ex->gsrc = d_imgs[0]; ex->gn = n; ex->gpitch = pitch; ex->gblur = initBlur; ex->gthresh = thresh; ex->glowest = lowestScale;
   return 0;
 }
 
-cs_extractor *cs_extractor_create(int w, int h, int numOctaves, int maxPts, int scaleUp)
+cs_extractor *cs_extractor_create_batch(int w, int h, int numOctaves, int maxPts, int scaleUp, int batch)
 {
+  if (batch < 1 || batch > CS_MAX_BATCH) { set_error("cs_extractor_create_batch: batch %d out of range (1..%d)", batch, CS_MAX_BATCH); return nullptr; }
   cs_extractor *ex = new cs_extractor();
   memset((void *)ex, 0, sizeof(*ex));
   new (&ex->pipe) Pipeline();
-  ex->w = w; ex->h = h; ex->numOctaves = numOctaves; ex->maxPts = maxPts; ex->scaleUp = scaleUp;
+  new (&ex->pipe2) Pipeline2();
+  ex->w = w; ex->h = h; ex->numOctaves = numOctaves; ex->maxPts = maxPts; ex->scaleUp = scaleUp; ex->B = batch;
   ex->pitch = ialignup(w, 128);
+  ex->legacy = legacy_mode();
+  if (ex->legacy && batch != 1) { set_error("the legacy pipeline takes one image at a time"); delete ex; return nullptr; }
   bool ok = cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && ex->pipe.init(w, h, numOctaves, scaleUp != 0, nullptr) == 0;
-  ok = ok && cudaMalloc((void **)&ex->d_img, (size_t)ex->pitch * h * sizeof(float)) == cudaSuccess;
-  ok = ok && cudaMalloc((void **)&ex->d_pts, (size_t)maxPts * sizeof(SiftPoint)) == cudaSuccess;
-  ok = ok && cudaMallocHost((void **)&ex->h_img, (size_t)w * h * sizeof(float)) == cudaSuccess;
-  ok = ok && cudaMallocHost((void **)&ex->h_pts, (size_t)maxPts * sizeof(SiftPoint)) == cudaSuccess;
-  ok = ok && cudaMallocHost((void **)&ex->h_counters, 4 * sizeof(unsigned int)) == cudaSuccess;
+  if (ex->legacy) ok = ok && ex->pipe.init(w, h, numOctaves, scaleUp != 0, nullptr) == 0;
+  else ok = ok && ex->pipe2.init(w, h, numOctaves, scaleUp != 0, batch, nullptr) == 0;
+  ok = ok && cudaMalloc((void **)&ex->d_img, (size_t)batch * ex->pitch * h * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMalloc((void **)&ex->d_pts, (size_t)batch * maxPts * sizeof(SiftPoint)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void **)&ex->h_img, (size_t)batch * w * h * sizeof(float)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void **)&ex->h_pts, (size_t)batch * maxPts * sizeof(SiftPoint)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void **)&ex->h_counters, (size_t)batch * CS_CNT_STRIDE * sizeof(unsigned int)) == cudaSuccess;
   if (!ok) {
     if (!cs::g_err[0]) set_error("cs_extractor_create: allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
     cs_extractor_destroy(ex);
@@ -979,13 +1063,18 @@ cs_extractor *cs_extractor_create(int w, int h, int numOctaves, int maxPts, int 
   return ex;
 }
 
+cs_extractor *cs_extractor_create(int w, int h, int numOctaves, int maxPts, int scaleUp)
+{
+  return cs_extractor_create_batch(w, h, numOctaves, maxPts, scaleUp, 1);
+}
+
 int cs_extractor_destroy(cs_extractor *ex)
 {
   if (!ex) return 0;
   if (ex->stream) cudaStreamSynchronize(ex->stream);
-  if (ex->gexec) cudaGraphExecDestroy(ex->gexec);
-  if (ex->graph) cudaGraphDestroy(ex->graph);
+  extractor_drop_graph(ex);
   ex->pipe.destroy();
+  ex->pipe2.destroy();
   if (ex->d_img) cudaFree(ex->d_img);
   if (ex->d_u8) cudaFree(ex->d_u8);
   if (ex->d_pts) cudaFree(ex->d_pts);
@@ -997,44 +1086,77 @@ int cs_extractor_destroy(cs_extractor *ex)
   return 0;
 }
 
+int cs_extractor_submit_device_batch(cs_extractor *ex, int n, const float *const *d_imgs, int pitch, double initBlur,
+                                     float thresh, float lowestScale)
+{
+  if (n < 1 || n > ex->B || !d_imgs) { set_error("cs_extractor_submit: batch of %d on an extractor built for %d", n, ex->B); return CS_E_ARG; }
+  ex->hostResults = false;
+  ex->lastN = n;
+  ex->submits++;
+  if (!ex->legacy)
+    for (int i = 0; i < n; i++)
+      if (!tensor_map_compatible(d_imgs[i], pitch)) {
+        set_error("cs_extractor_submit: image %d (%p, pitch %d) must be 16-byte aligned with a pitch that is a multiple of 4 "
+                  "floats (or use CUDASIFT_LEGACY=1)", i, (const void *)d_imgs[i], pitch);
+        return CS_E_ARG;
+      }
+  if (ex->gexec && (n != ex->gn || pitch != ex->gpitch || initBlur != ex->gblur || thresh != ex->gthresh || lowestScale != ex->glowest)) {
+    extractor_drop_graph(ex);                                           // parameters changed: re-capture
+    ex->submits = 2;
+  }
+  if (!ex->gexec && ex->submits == 2) extractor_capture(ex, n, d_imgs, pitch, initBlur, thresh, lowestScale);
+  if (ex->gexec) {
+    if (ex->legacy) {
+      if (d_imgs[0] != ex->gsrc) {
+        const float *src = d_imgs[0];
+        cudaKernelNodeParams kp = ex->gparams;
+        void *args[7];
+        for (int a = 0; a < 7; a++) args[a] = ex->gargs[a];
+        args[0] = (void *)&src;
+        kp.kernelParams = args;
+        CS_CUDA(cudaGraphExecKernelNodeSetParams(ex->gexec, ex->gnode, &kp));
+        ex->gsrc = d_imgs[0];
+      }
+    } else {
+      int r = ex->pipe2.fill_pyr_a(ex->gpa, n, d_imgs, pitch, initBlur);
+      if (r < 0) return r;
+      cudaKernelNodeParams kp = ex->gparams;
+      void *args[1] = {(void *)&ex->gpa};
+      kp.kernelParams = args;
+      CS_CUDA(cudaGraphExecKernelNodeSetParams(ex->gexec, ex->gnode, &kp));
+    }
+    CS_CUDA(cudaGraphLaunch(ex->gexec, ex->stream));
+    count_launch(ex->glaunches);
+    return 0;
+  }
+  return extractor_enqueue(ex, n, d_imgs, pitch, initBlur, thresh, lowestScale, nullptr, nullptr);
+}
+
 int cs_extractor_submit_device(cs_extractor *ex, const float *d_img, int pitch, double initBlur, float thresh,
                                float lowestScale)
 {
-  ex->hostResults = false;
-  ex->submits++;
-  if (ex->gexec && (pitch != ex->gpitch || initBlur != ex->gblur || thresh != ex->gthresh || lowestScale != ex->glowest)) {
-    cudaGraphExecDestroy(ex->gexec); cudaGraphDestroy(ex->graph);     // parameters changed: re-capture
-    ex->gexec = nullptr; ex->graph = nullptr; ex->submits = 2;
+  return cs_extractor_submit_device_batch(ex, 1, &d_img, pitch, initBlur, thresh, lowestScale);
+}
+
+int cs_extractor_submit_host_batch(cs_extractor *ex, int n, const float *const *h_imgs, double initBlur, float thresh,
+                                   float lowestScale)
+{
+  if (n < 1 || n > ex->B || !h_imgs) { set_error("cs_extractor_submit_host: batch of %d on an extractor built for %d", n, ex->B); return CS_E_ARG; }
+  const float *dptr[CS_MAX_BATCH];
+  for (int i = 0; i < n; i++) {
+    float *d = ex->d_img + (size_t)i * ex->pitch * ex->h;
+    CS_CUDA(cudaMemcpy2DAsync(d, (size_t)ex->pitch * sizeof(float), h_imgs[i], (size_t)ex->w * sizeof(float),
+                              (size_t)ex->w * sizeof(float), ex->h, cudaMemcpyHostToDevice, ex->stream));
+    dptr[i] = d;
   }
-  if (!ex->gexec && ex->submits == 2) extractor_capture(ex, d_img, pitch, initBlur, thresh, lowestScale);
-  if (ex->gexec) {
-    if (d_img != ex->gsrc) {
-      const float *src = d_img;
-      cudaKernelNodeParams kp = ex->gparams;
-      void *args[7];
-      for (int a = 0; a < 7; a++) args[a] = ex->gargs[a];
-      args[0] = (void *)&src;
-      kp.kernelParams = args;
-      CS_CUDA(cudaGraphExecKernelNodeSetParams(ex->gexec, ex->gnode, &kp));
-      ex->gsrc = d_img;
-    }
-    CS_CUDA(cudaGraphLaunch(ex->gexec, ex->stream));
-    count_launch(cs_extract_launches_per_image(ex->numOctaves, 0));
-    return 0;
-  }
-  int r = ex->pipe.enqueue(d_img, pitch, initBlur, thresh, lowestScale, ex->d_pts, ex->maxPts, ex->stream);
-  if (r < 0) return r;
-  CS_CUDA(cudaMemcpyAsync(ex->h_counters, ex->pipe.d_counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ex->stream));
-  return 0;
+  int r = cs_extractor_submit_device_batch(ex, n, dptr, ex->pitch, initBlur, thresh, lowestScale);
+  ex->hostResults = true;
+  return r;
 }
 
 int cs_extractor_submit_host(cs_extractor *ex, const float *h_img, double initBlur, float thresh, float lowestScale)
 {
-  CS_CUDA(cudaMemcpy2DAsync(ex->d_img, (size_t)ex->pitch * sizeof(float), h_img, (size_t)ex->w * sizeof(float),
-                            (size_t)ex->w * sizeof(float), ex->h, cudaMemcpyHostToDevice, ex->stream));
-  int r = cs_extractor_submit_device(ex, ex->d_img, ex->pitch, initBlur, thresh, lowestScale);
-  ex->hostResults = true;
-  return r;
+  return cs_extractor_submit_host_batch(ex, 1, &h_img, initBlur, thresh, lowestScale);
 }
 
 int cs_extractor_submit_host_u8(cs_extractor *ex, const unsigned char *h_img, double initBlur, float thresh,
@@ -1050,33 +1172,72 @@ int cs_extractor_submit_host_u8(cs_extractor *ex, const unsigned char *h_img, do
   return r;
 }
 
-int cs_extractor_wait(cs_extractor *ex)
+int cs_extractor_wait_batch(cs_extractor *ex, int *counts)
 {
   CS_CUDA(cudaStreamSynchronize(ex->stream));
-  int n = count_from_counters(ex->h_counters, ex->maxPts);
-  if (ex->hostResults && n > 0) {
-    CS_CUDA(cudaMemcpyAsync(ex->h_pts, ex->d_pts, sizeof(SiftPoint) * (size_t)n, cudaMemcpyDeviceToHost, ex->stream));
-    CS_CUDA(cudaStreamSynchronize(ex->stream));
+  const int n = ex->lastN > 0 ? ex->lastN : 1;
+  int total = 0;
+  bool copies = false;
+  for (int i = 0; i < n; i++) {
+    const int c = count_from_counters(ex->h_counters + (size_t)i * CS_CNT_STRIDE, ex->maxPts);
+    ex->lastCounts[i] = c;
+    if (counts) counts[i] = c;
+    total += c;
+    if (ex->hostResults && c > 0) {
+      CS_CUDA(cudaMemcpyAsync(ex->h_pts + (size_t)i * ex->maxPts, ex->d_pts + (size_t)i * ex->maxPts, sizeof(SiftPoint) * (size_t)c,
+                              cudaMemcpyDeviceToHost, ex->stream));
+      copies = true;
+    }
   }
-  ex->lastCount = n;
-  return n;
+  if (copies) CS_CUDA(cudaStreamSynchronize(ex->stream));
+  return total;
 }
 
-int cs_extractor_profile(cs_extractor *ex, const float *d_img, int pitch, double initBlur, float thresh,
-                         float lowestScale, float out_ms[5])
+int cs_extractor_wait(cs_extractor *ex) { return cs_extractor_wait_batch(ex, nullptr); }
+
+int cs_extractor_profile_batch(cs_extractor *ex, int n, const float *const *d_imgs, int pitch, double initBlur, float thresh,
+                               float lowestScale, float out_ms[5])
 {
+  if (n < 1 || n > ex->B) { set_error("cs_extractor_profile: bad batch"); return CS_E_ARG; }
   cudaEvent_t ev[5];
   for (int i = 0; i < 5; i++) CS_CUDA(cudaEventCreate(&ev[i]));
-  int r = ex->pipe.enqueue(d_img, pitch, initBlur, thresh, lowestScale, ex->d_pts, ex->maxPts, ex->stream, ev);
-  if (r < 0) return r;
-  CS_CUDA(cudaMemcpyAsync(ex->h_counters, ex->pipe.d_counters, 2 * sizeof(unsigned int), cudaMemcpyDeviceToHost, ex->stream));
+  ex->lastN = n;
+  int r = extractor_enqueue(ex, n, d_imgs, pitch, initBlur, thresh, lowestScale, ev, nullptr);
+  if (r < 0) { for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]); return r; }
   CS_CUDA(cudaStreamSynchronize(ex->stream));
   for (int i = 0; i < 4; i++) cudaEventElapsedTime(&out_ms[i], ev[i], ev[i + 1]);
   cudaEventElapsedTime(&out_ms[4], ev[0], ev[4]);
   for (int i = 0; i < 5; i++) cudaEventDestroy(ev[i]);
   ex->hostResults = false;
-  return count_from_counters(ex->h_counters, ex->maxPts);
+  return cs_extractor_wait_batch(ex, nullptr);
 }
+
+int cs_extractor_profile(cs_extractor *ex, const float *d_img, int pitch, double initBlur, float thresh,
+                         float lowestScale, float out_ms[5])
+{
+  return cs_extractor_profile_batch(ex, 1, &d_img, pitch, initBlur, thresh, lowestScale, out_ms);
+}
+
+// One pyramid level of image slot `slot` after the last submit (parity tests): copies lw x lh floats (packed)
+// to h_out; returns the level's width | height << 16, or a negative code.
+int cs_extractor_read_level(cs_extractor *ex, int slot, int level, float *h_out)
+{
+  CS_CUDA(cudaStreamSynchronize(ex->stream));
+  const float *src; int lw, lh, lp;
+  if (ex->legacy) {
+    if (slot != 0 || level < 0 || level >= ex->pipe.numLevels) { set_error("cs_extractor_read_level: bad level"); return CS_E_ARG; }
+    src = ex->pipe.lev[level]; lw = ex->pipe.lw[level]; lh = ex->pipe.lh[level]; lp = ex->pipe.lp[level];
+  } else {
+    if (slot < 0 || slot >= ex->B || level < 0 || level >= ex->pipe2.numLevels) { set_error("cs_extractor_read_level: bad level"); return CS_E_ARG; }
+    src = ex->pipe2.level(slot, level); lw = ex->pipe2.lw[level]; lh = ex->pipe2.lh[level]; lp = ex->pipe2.lp[level];
+  }
+  if (h_out)
+    CS_CUDA(cudaMemcpy2D(h_out, (size_t)lw * sizeof(float), src, (size_t)lp * sizeof(float), (size_t)lw * sizeof(float), lh,
+                         cudaMemcpyDeviceToHost));
+  return lw | (lh << 16);
+}
+
+int cs_extractor_count(cs_extractor *ex, int slot) { return (slot >= 0 && slot < CS_MAX_BATCH) ? ex->lastCounts[slot] : 0; }
 
 // ---- device timers (CUDA events on the extractor's own stream) ----
 void *cs_event_create(void)
@@ -1102,5 +1263,9 @@ double cs_event_elapsed_ms(void *a, void *b)
 void *cs_extractor_device_points(cs_extractor *ex) { return ex->d_pts; }
 void *cs_extractor_host_points(cs_extractor *ex) { return ex->h_pts; }
 float *cs_extractor_host_image(cs_extractor *ex) { return ex->h_img; }
+void *cs_extractor_device_points_at(cs_extractor *ex, int slot) { return ex->d_pts + (size_t)slot * ex->maxPts; }
+void *cs_extractor_host_points_at(cs_extractor *ex, int slot) { return ex->h_pts + (size_t)slot * ex->maxPts; }
+float *cs_extractor_host_image_at(cs_extractor *ex, int slot) { return ex->h_img + (size_t)slot * ex->w * ex->h; }
+int cs_max_batch(void) { return CS_MAX_BATCH; }
 
 }  // extern "C"

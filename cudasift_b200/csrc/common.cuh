@@ -8,6 +8,7 @@
 
 #include "../../include/cudaSift.h"
 #include "../../include/cudasift_b200.h"
+#include "tma.cuh"
 
 #define CS_NUM_SCALES 5                    // cudaSiftD.h:8
 #define CS_LAPLACE_S (CS_NUM_SCALES + 3)   // 8 blurred scales -> 7 DoG planes
@@ -65,6 +66,28 @@ int launch_scaleup(const float *src, float *dst, int w, int h, int pitch, int ne
                    cudaStream_t st);
 int launch_u8_to_float(const uint8_t *src, int srcPitch, float *dst, int dstPitch, int w, int h, cudaStream_t st);
 
+// ---- fused, batched pyramid (pyramid2.cu) ---------------------------------------------------
+#define CS_MAX_BATCH 32       // images per launch (input tensor maps travel as kernel parameters)
+#define CS_PA_OWN 240         // level-0 columns a CTA of kernel A owns
+struct PyrAParams {
+  CUtensorMap inMaps[CS_MAX_BATCH];   // input images, box 256 x 1
+  float *lev0; long long lev0Stride;  // image i writes lev0 + i * lev0Stride (floats)
+  float *lev1; long long lev1Stride;  // NULL: no ScaleDown (single octave)
+  int w, h, p0, w1, h1, p1;
+  Taps9 lp;
+  Taps5 sd;
+  int rowsPerCta, stripsX, rowBlocks;
+};
+int launch_pyr_a(const PyrAParams &p, int batch, cudaStream_t st);
+const void *pyr_a_func();            // the kernel function (graph node identification)
+struct PyrBParams {                   // chain of 1..3 ScaleDowns: img[0] -> img[1] -> ... -> img[steps]
+  float *img[4]; long long stride[4];
+  int w[4], h[4], pitch[4];
+  int steps;
+  Taps5 sd;
+};
+int launch_pyr_b(const PyrBParams &p, int batch, cudaStream_t st);
+
 // ---- detection ---------------------------------------------------------------------
 struct DetectLevel {
   const float *img;     // octave base image
@@ -92,16 +115,53 @@ int launch_detect(const DetectParams &p, cudaStream_t st);
 int launch_dog_planes(const float *base, float *dog, int w, int h, int pitch,
                       const LaplaceTaps &taps, cudaStream_t st);
 
+// ---- marching detector (detect2.cu): all octaves of a batch of images in one launch -----------
+#define CS_CNT_STRIDE 4       // per image: [0] primaries found, [1] total incl. secondaries, [2] spare, [3] overflowed cap cells
+#define CS_OVF_MAX 256        // overflowed (30x8 block, scale) cells recorded per image
+struct LaplaceTaps1 { float k[CS_LAPLACE_S][5]; };   // [scale][tap], tap 0 = centre
+struct D2Level {
+  int w, h;
+  float subsampling;
+  float lowestScale;          // lowestScale / subsampling, cudaSiftH.cu:213
+  LaplaceTaps1 taps;
+};
+struct Detect2Params {
+  D2Level lev[CS_MAX_LEVELS];
+  const CUtensorMap *maps;    // [image * CS_MAX_LEVELS + level]: octave base images, box 256 x 1
+  const uint4 *items;         // x: level | image << 8, y: x0, z: first tested row, w: rows per stream
+  int numItems;
+  float thresh, edgeLimit, factor;
+  SiftPoint *pts;             // image i writes pts + i * ptsStride
+  long long ptsStride;        // in records
+  unsigned int *counters;     // image i: counters + i * CS_CNT_STRIDE
+  unsigned int *sched;        // dynamic item scheduler (zeroed before the launch)
+  int maxPts;
+  // reference cap of 32 extrema per 30x8 block and scale (cudaSiftD.cu:1371,1379); cells == NULL: no cap
+  unsigned int *cells;        // packed 8-bit counters, image i: cells + i * cellWords
+  unsigned int *ovf;          // image i: ovf + i * CS_OVF_MAX
+  int cellWords;
+  int cellBase[CS_MAX_LEVELS], cellsX[CS_MAX_LEVELS];
+  const float *lev0Img[CS_MAX_LEVELS];   // level images of image slot 0 (fix-up kernel): slot i at + i * imgStride
+  long long imgStride;
+  int levPitch[CS_MAX_LEVELS];
+};
+int launch_detect2(const Detect2Params &p, int sms, cudaStream_t st);
+int launch_cap32_fixup(const Detect2Params &p, int batch, cudaStream_t st);
+#define CS_D2_STRIP 244       // tested columns per detector strip (multiple of 4: TMA box alignment)
+
 // ---- orientation + descriptor ---------------------------------------------------------
 struct DescribeParams {
-  cudaTextureObject_t tex[CS_MAX_LEVELS];   // indexed by log2(subsampling)
+  cudaTextureObject_t tex[CS_MAX_LEVELS];   // indexed by log2(subsampling); used when texArr == NULL
+  const cudaTextureObject_t *texArr;        // batch: [image * CS_MAX_LEVELS + level] (device memory)
   int numLevels;
-  SiftPoint *pts;
-  unsigned int *counters;
+  SiftPoint *pts;                           // image i: pts + i * ptsStride
+  long long ptsStride;
+  unsigned int *counters;                   // image i: counters + i * cntStride
+  int cntStride;
   int maxPts;
   float finestSubsampling;  // secondaries of this level are dropped (reference quirk Q1)
 };
-int launch_describe(const DescribeParams &p, int gridBlocks, cudaStream_t st);
+int launch_describe(const DescribeParams &p, int gridBlocks, cudaStream_t st, int batch = 1);
 int launch_rescale(SiftPoint *pts, const unsigned int *counters, int maxPts, float f,
                    cudaStream_t st);
 int launch_tex_probe(cudaTextureObject_t tex, const float *xs, const float *ys, int n,

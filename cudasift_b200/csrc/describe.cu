@@ -58,14 +58,17 @@ describe_kernel(const __grid_constant__ DescribeParams P)
   if (tx < 16) s_gauss16[tx] = __expf(-(tx - 7.5f) * (tx - 7.5f) / 128.0f);   // cudaSiftD.cu:318
   for (int i = tx; i < 32 * 33; i += DS_THREADS) (&s_hp[0][0])[i] = 0.0f;
 
-  const unsigned int found = P.counters[0];
+  const int img = blockIdx.y;
+  SiftPoint *const pts = P.pts + (size_t)img * P.ptsStride;
+  unsigned int *const counters = P.counters + (size_t)img * P.cntStride;
+  const unsigned int found = counters[0];
   const int numPrim = (int)min(found, (unsigned)P.maxPts);
 
   for (int pt = blockIdx.x; pt < numPrim; pt += gridDim.x) {
-    SiftPoint *sp = P.pts + pt;
+    SiftPoint *sp = pts + pt;
     const float px = sp->xpos, py = sp->ypos, pscale = sp->scale, psub = sp->subsampling;
     const int level = ((__float_as_int(psub) >> 23) & 0xff) - 127;   // subsampling = 2^level
-    const cudaTextureObject_t tex = P.tex[level];
+    const cudaTextureObject_t tex = P.texArr ? P.texArr[img * CS_MAX_LEVELS + level] : P.tex[level];
 
     // ------------------------------------------------------------ orientation histogram
     {
@@ -146,8 +149,8 @@ describe_kernel(const __grid_constant__ DescribeParams P)
           // Reference quirk Q1 (cudaSiftH.cu:115): secondary orientations of the finest
           // octave land beyond numPts and are never reported -> do not produce them.
           if (psub != P.finestSubsampling) {
-            atomicMax(&P.counters[1], (unsigned)numPrim);
-            unsigned int idx = atomicAdd(&P.counters[1], 1u);
+            atomicMax(&counters[1], (unsigned)numPrim);
+            unsigned int idx = atomicAdd(&counters[1], 1u);
             if (idx < (unsigned)P.maxPts) {
               s_ori[1] = __fmul_rn(11.25f, (pk2 < 0.0f ? __fadd_rn(pk2, 32.0f) : pk2));
               s_slot[1] = (int)idx;
@@ -252,7 +255,7 @@ describe_kernel(const __grid_constant__ DescribeParams P)
       if ((tx & 31) == 0) s_sums[tx >> 5] = sum;
       __syncthreads();
       float tsum2 = __fadd_rn(__fadd_rn(__fadd_rn(s_sums[0], s_sums[1]), s_sums[2]), s_sums[3]);
-      SiftPoint *out = P.pts + s_slot[k];
+      SiftPoint *out = pts + s_slot[k];
       out->data[tx] = __fmul_rn(t1, rsqrtf(tsum2));
       if (tx == 0) {
         out->xpos = __fmul_rn(px, psub);        // :410-414
@@ -270,9 +273,9 @@ describe_kernel(const __grid_constant__ DescribeParams P)
   }
 }
 
-int launch_describe(const DescribeParams &p, int gridBlocks, cudaStream_t st)
+int launch_describe(const DescribeParams &p, int gridBlocks, cudaStream_t st, int batch)
 {
-  describe_kernel<<<gridBlocks, DS_THREADS, 0, st>>>(p);
+  describe_kernel<<<dim3(gridBlocks, batch), DS_THREADS, 0, st>>>(p);
   count_launch();
   CS_CUDA(cudaGetLastError());
   return 0;

@@ -45,14 +45,7 @@ namespace cs {
 #define DT_SM_DOG ((CS_LAPLACE_S - 1) * DT_HP * DT_W) // 7 DoG planes, 16-byte chunks XOR-swizzled by the row pair
 #define DT_SMEM_BYTES ((DT_SM_IN + DT_SM_V + DT_SM_DOG) * 8)   // 56832 B -> 4 CTAs per SM
 
-typedef unsigned long long f32x2;   // two packed floats: lo = row r, hi = row r+8
-
-__device__ __forceinline__ f32x2 pk(float2 v) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y)); return r; }
-__device__ __forceinline__ float2 upk(f32x2 v) { float2 r; asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v)); return r; }
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// f32x2, pk/upk, fma2/mul2/add2/sub2: tma.cuh (lo = row r, hi = row r+8)
 
 // cudaSiftD.cu:1769-1772 / 1779-1788: sum = k0*c; sum += kj*(x[-j]+x[+j]), j=1..4.
 // SASS: FMUL(k1,p1); FFMA(k0,c); FFMA(k2,p2); FFMA(k3,p3); FFMA(k4,p4)  -- here on both halves at once.
@@ -446,13 +439,16 @@ int g_detect_skip = 0;
 template <int T, int NC, int VR, int MINB>
 static int launch_variant(const DetectParams &p, cudaStream_t st)
 {
-  static int sms = 0;
-  if (sms == 0) {
+  // per device: cudaFuncSetAttribute applies to the current device only, and SM counts may differ
+  static int smsOf[64];
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  dev &= 63;
+  if (smsOf[dev] == 0) {
     CS_CUDA(cudaFuncSetAttribute(detect_kernel<T, NC, VR, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES));
-    int dev = 0;
-    CS_CUDA(cudaGetDevice(&dev));
-    CS_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CS_CUDA(cudaDeviceGetAttribute(&smsOf[dev], cudaDevAttrMultiProcessorCount, dev));
   }
+  const int sms = smsOf[dev];
   const int grid = p.totalTiles < MINB * sms ? p.totalTiles : MINB * sms;
   detect_kernel<T, NC, VR, MINB><<<grid, T, DT_SMEM_BYTES, st>>>(p);
   return 0;
@@ -513,10 +509,13 @@ dog_planes_kernel(const float *__restrict__ img, float *__restrict__ dog, int w,
 
 int launch_dog_planes(const float *base, float *dog, int w, int h, int pitch, const LaplaceTaps &taps, cudaStream_t st)
 {
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64];
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  dev &= 63;
+  if (!configured[dev]) {
     CS_CUDA(cudaFuncSetAttribute(dog_planes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DT_SMEM_BYTES));
-    configured = true;
+    configured[dev] = true;
   }
   int tilesX = idivup(w, DT_W - 2), tilesY = idivup(h, DT_H - 2);
   dog_planes_kernel<<<tilesX * tilesY, DT_THREADS, DT_SMEM_BYTES, st>>>(base, dog, w, h, pitch, tilesX, taps);

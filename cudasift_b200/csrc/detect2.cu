@@ -1,0 +1,420 @@
+// detect2.cu -- marching detector: 8-scale blur + DoG + 3x3x3 extrema + sub-pixel refinement, all octaves of
+// a whole BATCH of images in one launch.
+//
+// Behavioural spec: reference LaplaceMultiMem (cudaSiftD.cu:1753-1793, host :460-487) and
+// FindPointsMultiNew (cudaSiftD.cu:1292-1431, host :489-514).  Same per-pixel arithmetic as detect.cu
+// (pinned to the reference's sm_100 SASS: which products are fused, the order of the sums), new dataflow:
+//
+//  * A work item is a column strip (256 staged columns -> 248 DoG columns -> 244 tested columns) times a
+//    range of rows of one octave of one image.  The CTA marches down the rows; nothing is recomputed
+//    vertically: the 9-row window of every column lives in REGISTERS and slides by one row per step.
+//  * Packed FP32 (FFMA2/FADD2): the two halves of every register pair are two ROW STREAMS of the same item
+//    (row y and row y + hs), so all horizontal neighbours are whole aligned pairs.
+//  * Input rows arrive by TMA (cp.async.bulk.tensor.2d, one 256x1 box per row and stream, row index clamped
+//    by the issuing thread, columns clamped by the reading thread) into an 8-deep ring -> no address
+//    arithmetic and no global loads in the loop.
+//  * Vertical pass: thread = 2 columns x 4 scales (warps 0-3: scales 0-3, warps 4-7: scales 4-7); the 20 taps
+//    are 20 registers (FFMA2 takes a scalar operand that it broadcasts to both halves); results go to shared
+//    memory once (STS.64).
+//  * Horizontal pass + DoG: lane = (scale, 8 columns); 8 conflict-free LDS.128 fetch the 16 pairs, the DoG
+//    difference takes the neighbouring scale from the neighbouring lane (shuffle), the 7 DoG planes of the row
+//    pair go to a 4-row ring in shared memory (only 3 rows of DoG ever exist).
+//  * |DoG| > thresh is decided on the register copies; flagged (pixel, plane) candidates are listed and tested
+//    two steps later, when the rows above and below exist, by whichever thread is free.
+//
+// Shared memory per row pair and step: 128 (vertical STS) + 256 (horizontal LDS) + 128 (shuffles) + 112 (DoG
+// STS) wavefronts for 2 x 244 pixels x 8 scales = 1.3 wavefronts per pixel (detect.cu: 2.7).
+#include "common.cuh"
+
+namespace cs {
+
+#define D2_THREADS 256
+#define D2_IW 256            // staged input columns per strip (one TMA box row)
+#define D2_TESTED CS_D2_STRIP // tested DoG columns per strip: 1..244 (DoG column d <-> input column d + 4); a multiple of 4,
+                             // because TMA wants the first column of a box (x0 - 4) on a 16-byte boundary
+#define D2_NS 8              // input ring depth (row pairs)
+#define D2_VROW2 258         // float2 per (scale) row of vertical results: 256 + one 16-byte pad
+#define D2_VBUF2 (8 * D2_VROW2)
+#define D2_RROWF 500         // floats per DoG plane row in the ring: 248 pairs + one 16-byte pad
+#define D2_RSLOTF (7 * D2_RROWF)
+#define D2_LCAP 510          // candidate list capacity per step (more: the step is scanned exhaustively)
+#define D2_KQ 32             // keypoints parked per item before the slots are allocated
+#define D2_SMEM_IN (D2_NS * 2 * D2_IW * 4)            // 16384
+#define D2_SMEM_V (2 * D2_VBUF2 * 8)                  // 33024
+#define D2_SMEM_RING (4 * D2_RSLOTF * 4)              // 56000
+#define D2_SMEM_LIST (4 * 512 * 2)                    // 4096
+#define D2_SMEM_BYTES (D2_SMEM_IN + D2_SMEM_V + D2_SMEM_RING + D2_SMEM_LIST)   // 109504 -> 2 CTAs per SM
+
+// cudaSiftD.cu:1769-1772 / 1779-1788: sum = k0*c; sum += kj*(x[-j]+x[+j]), j=1..4.
+// SASS: FMUL(k1,p1); FFMA(k0,c); FFMA(k2,p2); FFMA(k3,p3); FFMA(k4,p4)  -- here on both halves at once.
+// A tap is ONE register: pk2(k, k) folds into the scalar-broadcast operand form of FFMA2 (Rk.F32).
+__device__ __forceinline__ f32x2 d2_sym9(const float (&k)[5], f32x2 c, f32x2 p1, f32x2 p2, f32x2 p3, f32x2 p4)
+{
+  f32x2 s = mul2(pk2(k[1], k[1]), p1);
+  s = fma2(pk2(k[0], k[0]), c, s);
+  s = fma2(pk2(k[2], k[2]), p2, s);
+  s = fma2(pk2(k[3], k[3]), p3, s);
+  s = fma2(pk2(k[4], k[4]), p4, s);
+  return s;
+}
+
+// One step of the vertical pass: the newest input row pair enters window slot PH (the oldest one leaves),
+// then this thread's 4 scales of both columns are written to the vertical-result buffer.
+template <int PH>
+__device__ __forceinline__ void d2_vertical(f32x2 (&W0)[9], f32x2 (&W1)[9], f32x2 n0, f32x2 n1,
+                                            const float (&kv)[4][5], float2 *vdst)
+{
+#define D2_WI(i) ((PH + 1 + (i)) % 9)
+  W0[PH] = n0;
+  W1[PH] = n1;
+  {
+    const f32x2 c = W0[D2_WI(4)];
+    const f32x2 p1 = add2(W0[D2_WI(3)], W0[D2_WI(5)]), p2 = add2(W0[D2_WI(2)], W0[D2_WI(6)]);
+    const f32x2 p3 = add2(W0[D2_WI(1)], W0[D2_WI(7)]), p4 = add2(W0[D2_WI(0)], W0[D2_WI(8)]);
+#pragma unroll
+    for (int s = 0; s < 4; s++) vdst[s * D2_VROW2] = upk(d2_sym9(kv[s], c, p1, p2, p3, p4));
+  }
+  {
+    const f32x2 c = W1[D2_WI(4)];
+    const f32x2 p1 = add2(W1[D2_WI(3)], W1[D2_WI(5)]), p2 = add2(W1[D2_WI(2)], W1[D2_WI(6)]);
+    const f32x2 p3 = add2(W1[D2_WI(1)], W1[D2_WI(7)]), p4 = add2(W1[D2_WI(0)], W1[D2_WI(8)]);
+#pragma unroll
+    for (int s = 0; s < 4; s++) vdst[s * D2_VROW2 + 128] = upk(d2_sym9(kv[s], c, p1, p2, p3, p4));
+  }
+#undef D2_WI
+}
+
+struct D2Keypoint { float x, y, scale, sharpness, edgeness, subsampling; unsigned int tag; };
+
+__device__ __forceinline__ void d2_store_keypoint(SiftPoint *pts, int maxPts, unsigned int idx, const D2Keypoint &kp)
+{
+  if (idx >= (unsigned)maxPts) idx = maxPts - 1;    // cudaSiftD.cu:1421
+  SiftPoint *q = pts + idx;
+  q->xpos = kp.x;
+  q->ypos = kp.y;
+  q->scale = kp.scale;
+  q->sharpness = kp.sharpness;
+  q->edgeness = kp.edgeness;
+  q->subsampling = kp.subsampling;
+  q->empty[0] = __uint_as_float(kp.tag);            // integer position of the extremum (cap32 bookkeeping)
+}
+
+// cudaSiftD.cu:1383-1429.  v[p][dy][dx]: the 3x3x3 DoG neighbourhood, candidate at [1][1][1].
+__device__ __forceinline__ void d2_refine(const float (&v)[3][3][3], int gx, int gy, int scale, float subsampling,
+                                       float lowestScale, float edgeLimit, float factor, unsigned int tag,
+                                       D2Keypoint *s_kq, int *s_kn, SiftPoint *pts, unsigned int *counter, int maxPts)
+{
+  const float val = v[1][1][1];
+  float two = __fadd_rn(val, val);
+  float dxx = __fsub_rn(__fsub_rn(two, v[1][1][0]), v[1][1][2]);
+  float dyy = __fsub_rn(__fsub_rn(two, v[1][0][1]), v[1][2][1]);
+  float dxy = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(v[1][2][2], v[1][0][0]), v[1][0][2]), v[1][2][0]));
+  float tra = __fadd_rn(dxx, dyy);
+  float det = __fmaf_rn(dxx, dyy, -__fmul_rn(dxy, dxy));
+  float tra2 = __fmul_rn(tra, tra);
+  if (!(tra2 < __fmul_rn(edgeLimit, det))) return;
+  float edge = __fdividef(tra2, det);
+  float dx = __fmul_rn(0.5f, __fsub_rn(v[1][1][2], v[1][1][0]));
+  float dy = __fmul_rn(0.5f, __fsub_rn(v[1][2][1], v[1][0][1]));
+  float ds = __fmul_rn(0.5f, __fsub_rn(v[0][1][1], v[2][1][1]));
+  float dss = __fsub_rn(__fsub_rn(two, v[2][1][1]), v[0][1][1]);
+  float dxs = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(v[2][1][2], v[0][1][0]), v[0][1][2]), v[2][1][0]));
+  float dys = __fmul_rn(0.25f, __fsub_rn(__fsub_rn(__fadd_rn(v[2][2][1], v[0][0][1]), v[2][0][1]), v[0][2][1]));
+  float idxx = __fmaf_rn(dyy, dss, -__fmul_rn(dys, dys));
+  float idxy = __fmaf_rn(dys, dxs, -__fmul_rn(dxy, dss));
+  float idxs = __fmaf_rn(dxy, dys, -__fmul_rn(dyy, dxs));
+  float det3 = __fmaf_rn(idxs, dxs, __fmaf_rn(idxx, dxx, __fmul_rn(idxy, dxy)));
+  float idet = __fdividef(1.0f, det3);
+  float idyy = __fmaf_rn(dxx, dss, -__fmul_rn(dxs, dxs));
+  float idys = __fmaf_rn(dxy, dxs, -__fmul_rn(dxx, dys));
+  float idss = det;
+  float pdx = __fmul_rn(idet, __fmaf_rn(ds, idxs, __fmaf_rn(dx, idxx, __fmul_rn(dy, idxy))));
+  float pdy = __fmul_rn(idet, __fmaf_rn(ds, idys, __fmaf_rn(dy, idyy, __fmul_rn(dx, idxy))));
+  float pds = __fmul_rn(idet, __fmaf_rn(idss, ds, __fmaf_rn(dx, idxs, __fmul_rn(dy, idys))));
+  if (pdx < -0.5f || pdx > 0.5f || pdy < -0.5f || pdy > 0.5f || pds < -0.5f || pds > 0.5f) {
+    pdx = __fdividef(dx, dxx);
+    pdy = __fdividef(dy, dyy);
+    pds = __fdividef(ds, dss);
+  }
+  float dsum = __fmaf_rn(ds, pds, __fmaf_rn(dx, pdx, __fmul_rn(dy, pdy)));
+  float sc = __fmul_rn(powf(2.0f, __fdiv_rn((float)scale, (float)CS_NUM_SCALES)), exp2f(__fmul_rn(pds, factor)));
+  if (!(sc >= lowestScale)) return;
+  D2Keypoint kp;
+  kp.x = __fadd_rn((float)gx, pdx);
+  kp.y = __fadd_rn((float)gy, pdy);
+  kp.scale = sc;
+  kp.sharpness = __fmaf_rn(dsum, 0.5f, val);
+  kp.edgeness = edge;
+  kp.subsampling = subsampling;
+  kp.tag = tag;
+  const int q = atomicAdd(s_kn, 1);
+  if (q < D2_KQ) s_kq[q] = kp;
+  else d2_store_keypoint(pts, maxPts, atomicAdd(counter, 1u), kp);
+}
+
+__global__ void __launch_bounds__(D2_THREADS, 2)
+detect2_kernel(const __grid_constant__ Detect2Params P)
+{
+  extern __shared__ __align__(128) unsigned char d2_smem[];
+  float *s_in = reinterpret_cast<float *>(d2_smem);                                         // [slot][stream][256]
+  float2 *s_v = reinterpret_cast<float2 *>(d2_smem + D2_SMEM_IN);                           // [buf][scale][258]
+  float *s_ring = reinterpret_cast<float *>(d2_smem + D2_SMEM_IN + D2_SMEM_V);              // [slot][plane][500]
+  unsigned short *s_list = reinterpret_cast<unsigned short *>(d2_smem + D2_SMEM_IN + D2_SMEM_V + D2_SMEM_RING);
+  __shared__ __align__(8) uint64_t s_full[D2_NS];
+  __shared__ int s_cnt[4];
+  __shared__ int s_kn, s_next;
+  __shared__ D2Keypoint s_kq[D2_KQ];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int half = tid >> 7, cl = tid & 127;              // vertical role: columns cl, cl+128, scales 4*half..+3
+  const int hs_ = lane & 7, cgl = lane >> 3;              // horizontal role: scale hs_, column group cg
+  const int cg = 4 * warp + cgl;
+  const float thresh = P.thresh;
+
+  int item = blockIdx.x;
+  unsigned int req = 0;
+  if (tid == 0) req = gridDim.x + atomicAdd(P.sched, 1u);
+
+  while (item < P.numItems) {
+    // ------------------------------------------------------------------ item set-up
+    const uint4 it = __ldg(P.items + item);
+    const int level = it.x & 0xff, img = it.x >> 8;
+    const int x0 = (int)it.y, ry0 = (int)it.z, hs = (int)it.w;
+    const D2Level &L = P.lev[level];
+    const int w = L.w, h = L.h;
+    const CUtensorMap *map = P.maps + (size_t)img * CS_MAX_LEVELS + level;
+    SiftPoint *pts = P.pts + (size_t)img * P.ptsStride;
+    unsigned int *counters = P.counters + (size_t)img * CS_CNT_STRIDE;
+    const int nsteps = hs + 2;                            // DoG rows ry0-1+k (stream A), ry0+hs-1+k (stream B), k < nsteps
+    const int nrows = 8 + nsteps;                         // input rows per stream: ry0-5+i (A), i < nrows
+
+    __syncthreads();     // previous item's last extrema pass and keypoint flush are complete
+    if (tid == 0) {
+      for (int i = 0; i < D2_NS; i++) mbarrier_init(&s_full[i], 1);
+      mbarrier_init_fence();
+      s_cnt[0] = s_cnt[1] = s_cnt[2] = s_cnt[3] = 0;
+      s_kn = 0;
+      s_next = (int)req;                                  // requested during the previous item
+      req = gridDim.x + atomicAdd(P.sched, 1u);
+    }
+    __syncthreads();     // barriers initialised, next item index published
+    if (tid == 0) {
+      tensormap_acquire(map);
+      for (int i = 0; i < D2_NS; i++) {                   // prologue rows: all in flight at once
+        mbarrier_expect_tx(&s_full[i], 2 * D2_IW * 4);
+        tma_load_2d(s_in + (2 * i) * D2_IW, map, x0 - 4, min(max(ry0 - 5 + i, 0), h - 1), &s_full[i]);
+        tma_load_2d(s_in + (2 * i + 1) * D2_IW, map, x0 - 4, min(max(ry0 + hs - 5 + i, 0), h - 1), &s_full[i]);
+      }
+    }
+    // columns this thread reads from a staged row (clamped to the image: cudaSiftD.cu:1764-1767)
+    const int ci0 = min(max(x0 - 4 + cl, 0), w - 1) - (x0 - 4);
+    const int ci1 = min(max(x0 - 4 + cl + 128, 0), w - 1) - (x0 - 4);
+    // horizontal role
+    const bool hact = cg < 31 && x0 + 8 * cg <= w - 1;    // this lane's 8 DoG columns start inside the image
+    const unsigned hmask = __ballot_sync(0xffffffffu, hact);
+    float kh[5], kv[4][5];                                // taps: this lane's scale (horizontal), this half's 4 scales (vertical)
+#pragma unroll
+    for (int j = 0; j < 5; j++) kh[j] = L.taps.k[hs_][j];
+#pragma unroll
+    for (int s = 0; s < 4; s++)
+#pragma unroll
+      for (int j = 0; j < 5; j++) kv[s][j] = L.taps.k[4 * half + s][j];
+    unsigned colok = 0;                                   // which of the 8 DoG columns may hold an extremum
+#pragma unroll
+    for (int d = 0; d < 8; d++) {
+      const int dc = 8 * cg + d;
+      if (dc >= 1 && dc <= D2_TESTED && x0 + dc <= w - 2) colok |= 1u << d;
+    }
+
+    f32x2 W0[9], W1[9];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      mbarrier_wait(&s_full[i], 0);
+      const float *ra = s_in + (2 * i) * D2_IW, *rb = ra + D2_IW;
+      W0[i] = pk2(ra[ci0], rb[ci0]);
+      W1[i] = pk2(ra[ci1], rb[ci1]);
+    }
+    W0[8] = 0ull; W1[8] = 0ull;
+    __syncthreads();                                      // every thread has read the prologue rows
+    if (tid == 0) {
+      for (int i = 0; i < D2_NS; i++) {
+        if (8 + i < nrows) {
+          mbarrier_expect_tx(&s_full[i], 2 * D2_IW * 4);
+          tma_load_2d(s_in + (2 * i) * D2_IW, map, x0 - 4, min(max(ry0 + 3 + i, 0), h - 1), &s_full[i]);
+          tma_load_2d(s_in + (2 * i + 1) * D2_IW, map, x0 - 4, min(max(ry0 + hs + 3 + i, 0), h - 1), &s_full[i]);
+        }
+      }
+    }
+
+    int ph = 8;                                           // window slot of the newest row: (8 + k) % 9
+    for (int k = 0; k <= nsteps; k++) {
+      const bool compute = k < nsteps;
+      const int q = k & 3;
+      if (compute) {
+        // ---------------------------------------------------------------- vertical pass
+        const int slot = k & (D2_NS - 1);
+        mbarrier_wait(&s_full[slot], ((8 + k) >> 3) & 1);
+        const float *ra = s_in + (2 * slot) * D2_IW, *rb = ra + D2_IW;
+        const f32x2 n0 = pk2(ra[ci0], rb[ci0]), n1 = pk2(ra[ci1], rb[ci1]);
+        float2 *vdst = s_v + (k & 1) * D2_VBUF2 + (4 * half) * D2_VROW2 + cl;
+#define D2_CASE(p) case p: d2_vertical<p>(W0, W1, n0, n1, kv, vdst); break;
+        switch (ph) {
+          D2_CASE(0) D2_CASE(1) D2_CASE(2) D2_CASE(3) D2_CASE(4) D2_CASE(5) D2_CASE(6) D2_CASE(7) D2_CASE(8)
+        }
+#undef D2_CASE
+        ph = (ph == 8) ? 0 : ph + 1;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        s_cnt[(k + 1) & 3] = 0;                           // list of step k+1 (last read during step k-1)
+        const int slot = k & (D2_NS - 1);
+        if (compute && 16 + k < nrows) {                  // the slot just consumed: refill with the row 8 steps ahead
+          mbarrier_expect_tx(&s_full[slot], 2 * D2_IW * 4);
+          tma_load_2d(s_in + (2 * slot) * D2_IW, map, x0 - 4, min(max(ry0 + 11 + k, 0), h - 1), &s_full[slot]);
+          tma_load_2d(s_in + (2 * slot + 1) * D2_IW, map, x0 - 4, min(max(ry0 + hs + 11 + k, 0), h - 1), &s_full[slot]);
+        }
+      }
+      if (compute && hact) {
+        // -------------------------------------------------------------- horizontal pass + DoG
+        const float4 *src = reinterpret_cast<const float4 *>(s_v + (k & 1) * D2_VBUF2 + hs_ * D2_VROW2 + 8 * cg);
+        f32x2 V[16];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float4 t4 = src[j];
+          V[2 * j] = pk2(t4.x, t4.y);
+          V[2 * j + 1] = pk2(t4.z, t4.w);
+        }
+        f32x2 dg[8];
+#pragma unroll
+        for (int d = 0; d < 8; d++) {
+          const f32x2 o = d2_sym9(kh, V[d + 4], add2(V[d + 3], V[d + 5]), add2(V[d + 2], V[d + 6]),
+                                   add2(V[d + 1], V[d + 7]), add2(V[d], V[d + 8]));
+          const float2 of = upk(o);
+          const float plo = __shfl_up_sync(hmask, of.x, 1), phi = __shfl_up_sync(hmask, of.y, 1);
+          dg[d] = sub2(o, pk2(plo, phi));                 // blur[s] - blur[s-1]: DoG plane s-1 (cudaSiftD.cu:1790)
+        }
+        if (hs_ >= 1) {
+          float4 *dst = reinterpret_cast<float4 *>(s_ring + q * D2_RSLOTF + (hs_ - 1) * D2_RROWF + 16 * cg);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float2 a = upk(dg[2 * j]), b = upk(dg[2 * j + 1]);
+            dst[j] = make_float4(a.x, a.y, b.x, b.y);
+          }
+        }
+        if (hs_ >= 2 && hs_ <= 6 && k >= 1 && k <= hs) {  // planes 1..5, rows that are tested
+          float m = 0.0f;
+#pragma unroll
+          for (int d = 0; d < 8; d++) {
+            const float2 a = upk(dg[d]);
+            m = fmaxf(m, fmaxf(fabsf(a.x), fabsf(a.y)));
+          }
+          if (m > thresh) {
+            const bool okA = ry0 - 1 + k <= h - 2, okB = ry0 + hs - 1 + k <= h - 2;
+            unsigned bits = 0;
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+              const float2 a = upk(dg[d]);
+              if (okA && fabsf(a.x) > thresh) bits |= 1u << d;
+              if (okB && fabsf(a.y) > thresh) bits |= 0x100u << d;
+            }
+            bits &= colok | (colok << 8);
+            if (bits) {
+              int at = atomicAdd(&s_cnt[q], __popc(bits));
+              while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (at < D2_LCAP) s_list[q * 512 + at] = (unsigned short)((8 * cg + (b & 7)) | ((hs_ - 1) << 8) | ((b >> 3) << 11));
+                at++;
+              }
+            }
+          }
+        }
+      }
+      if (k >= 2) {
+        // -------------------------------------------------------------- extrema of step j = k - 2
+        const int j = k - 2, qj = j & 3;
+        int n = s_cnt[qj];
+        const bool scan = n > D2_LCAP;                    // list overflow: test every pixel of the row pair
+        if (scan) n = 2 * CS_NUM_SCALES * D2_TESTED;
+        const float *rm = s_ring + ((j + 3) & 3) * D2_RSLOTF, *r0 = s_ring + qj * D2_RSLOTF, *rp = s_ring + ((j + 1) & 3) * D2_RSLOTF;
+        for (int i = tid; i < n; i += D2_THREADS) {
+          int dc, p, hf;
+          if (!scan) {
+            const int e = s_list[qj * 512 + i];
+            dc = e & 255; p = (e >> 8) & 7; hf = e >> 11;
+          } else {
+            hf = i / (CS_NUM_SCALES * D2_TESTED);
+            const int r = i - hf * (CS_NUM_SCALES * D2_TESTED);
+            p = r / D2_TESTED;
+            dc = 1 + r - p * D2_TESTED;
+            p += 1;
+            const int gy_ = (hf ? ry0 + hs - 1 : ry0 - 1) + j;
+            if (j < 1 || j > hs || gy_ > h - 2 || x0 + dc > w - 2) continue;
+          }
+          const int o = p * D2_RROWF + 2 * dc + hf;
+          const float c = r0[o];
+          if (!(fabsf(c) > thresh)) continue;
+          float v[3][3][3];
+#pragma unroll
+          for (int pp = 0; pp < 3; pp++)
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) {
+              const int oo = o + (pp - 1) * D2_RROWF + 2 * (dx - 1);
+              v[pp][0][dx] = rm[oo];
+              v[pp][1][dx] = r0[oo];
+              v[pp][2][dx] = rp[oo];
+            }
+          bool mx = true, mn = true;
+#pragma unroll
+          for (int pp = 0; pp < 3; pp++)
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+              for (int dx = 0; dx < 3; dx++)
+                if (pp != 1 || dy != 1 || dx != 1) { mx = mx && (c > v[pp][dy][dx]); mn = mn && (c < v[pp][dy][dx]); }
+          if (c > 0.0f ? mx : mn) {
+            const int gx = x0 + dc, gy = (hf ? ry0 + hs - 1 : ry0 - 1) + j;
+            const unsigned int tag = (unsigned)gx | ((unsigned)gy << 13) | ((unsigned)(p - 1) << 26) | ((unsigned)level << 29);
+            if (P.cells) {                                // extrema per 30x8 block and scale (reference cap, cudaSiftD.cu:1371)
+              const int cell = P.cellBase[level] + ((gy >> 3) * P.cellsX[level] + gx / 30) * CS_NUM_SCALES + (p - 1);
+              unsigned int *cw = P.cells + (size_t)img * P.cellWords + (cell >> 2);
+              const unsigned old = atomicAdd(cw, 1u << (8 * (cell & 3)));
+              if (((old >> (8 * (cell & 3))) & 0xff) == 32) {      // the 33rd extremum of this cell
+                const unsigned at = atomicAdd(&counters[3], 1u);
+                if (at < CS_OVF_MAX) P.ovf[(size_t)img * CS_OVF_MAX + at] = (unsigned)cell;
+              }
+            }
+            d2_refine(v, gx, gy, p - 1, L.subsampling, L.lowestScale, P.edgeLimit, P.factor, tag, s_kq, &s_kn, pts,
+                      &counters[0], P.maxPts);
+          }
+        }
+      }
+    }
+    __syncthreads();
+    {
+      const int nkq = min(s_kn, D2_KQ);
+      if (tid < nkq) d2_store_keypoint(pts, P.maxPts, atomicAdd(&counters[0], 1u), s_kq[tid]);
+    }
+    item = s_next;
+  }
+}
+
+static int g_d2_configured[64];
+
+int launch_detect2(const Detect2Params &p, int sms, cudaStream_t st)
+{
+  if (p.numItems <= 0) return 0;
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && !g_d2_configured[dev]) {      // per device: cudaFuncSetAttribute applies to the current device only
+    CS_CUDA(cudaFuncSetAttribute(detect2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BYTES));
+    g_d2_configured[dev] = 1;
+  }
+  const int grid = p.numItems < 2 * sms ? p.numItems : 2 * sms;
+  detect2_kernel<<<grid, D2_THREADS, D2_SMEM_BYTES, st>>>(p);
+  count_launch();
+  CS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace cs

@@ -33,8 +33,11 @@ const char *cs_version(void);
 int cs_init(int device);
 /* Number of kernels this library has launched so far in this process. */
 unsigned long long cs_launch_count(void);
-/* Tuning hook (benchmarks only): key "detect_variant" selects one of the compiled detector
- * configurations for pipelines created afterwards.  Returns 0, or CS_E_ARG for an unknown key. */
+/* Tuning hook (benchmarks and tests only).  Keys: "legacy" (1 = the round-1 per-image kernels for pipelines
+ * created afterwards, 0 = the batched TMA pipeline), "cap32" (0 = do not reproduce the reference's cap of 32
+ * extrema per 30x8 block and scale, cudaSiftD.cu:1371), "d2_hs" / "pa_rows" (rows per detector stream / per CTA
+ * of the first pyramid kernel, 0 = automatic), "detect_variant" / "detect_skip" (legacy detector).
+ * Returns 0, or CS_E_ARG for an unknown key. */
 int cs_set_tuning(const char *key, int value);
 /* Number of launches one steady-state cs_extractor_submit_* / cs_match issues. */
 int cs_extract_launches_per_image(int numOctaves, int scaleUp);
@@ -124,12 +127,38 @@ int cs_extractor_submit_host(cs_extractor *ex, const float *h_img,
 int cs_extractor_submit_host_u8(cs_extractor *ex, const unsigned char *h_img,
                                 double initBlur, float thresh, float lowestScale);
 /* One image, synchronously, with CUDA events at the stage boundaries of the extractor's
- * stream: out_ms = {LowPass, ScaleDown chain, detect (blur+DoG+extrema), describe
+ * stream: out_ms = {LowPass (+ first ScaleDown), ScaleDown chain, detect (blur+DoG+extrema), describe
  * (orientation+descriptor), total}.  Returns numPts. */
 int cs_extractor_profile(cs_extractor *ex, const float *d_img, int pitch, double initBlur,
                          float thresh, float lowestScale, float out_ms[5]);
 /* Wait for the last submit; returns numPts. */
 int cs_extractor_wait(cs_extractor *ex);
+
+/* ---- batched extraction: what replaces the caller's loop over images (mainSift.cpp:65-69) ----
+ * One submit runs every stage ONCE for up to `batch` images of the same size: the pyramid, the detector
+ * (all octaves of all images) and the descriptor kernel each see the whole batch in one launch.
+ * cs_max_batch() = the largest batch one extractor takes.  Image i uses record slot i (maxPts records each). */
+int cs_max_batch(void);
+cs_extractor *cs_extractor_create_batch(int width, int height, int numOctaves, int maxPts, int scaleUp, int batch);
+/* d_imgs: n device images (16-byte aligned, common pitch, a multiple of 4 floats). */
+int cs_extractor_submit_device_batch(cs_extractor *ex, int n, const float *const *d_imgs, int pitch,
+                                     double initBlur, float thresh, float lowestScale);
+/* h_imgs: n host images of width*height packed floats; copies are enqueued on the extractor's stream. */
+int cs_extractor_submit_host_batch(cs_extractor *ex, int n, const float *const *h_imgs,
+                                   double initBlur, float thresh, float lowestScale);
+/* Wait for the last submit: counts[i] = numPts of image i (counts may be NULL); after a host submit the records
+ * of every image are in its pinned slot (cs_extractor_host_points_at).  Returns the sum of the counts. */
+int cs_extractor_wait_batch(cs_extractor *ex, int *counts);
+int cs_extractor_count(cs_extractor *ex, int slot);
+void *cs_extractor_device_points_at(cs_extractor *ex, int slot);
+void *cs_extractor_host_points_at(cs_extractor *ex, int slot);
+float *cs_extractor_host_image_at(cs_extractor *ex, int slot);
+/* Stage times of one batch (see cs_extractor_profile); returns the sum of the counts. */
+int cs_extractor_profile_batch(cs_extractor *ex, int n, const float *const *d_imgs, int pitch, double initBlur,
+                               float thresh, float lowestScale, float out_ms[5]);
+/* Parity tests: pyramid level `level` of image slot `slot` as left by the last submit, packed into h_out
+ * (may be NULL); returns width | height << 16 of that level. */
+int cs_extractor_read_level(cs_extractor *ex, int slot, int level, float *h_out);
 void *cs_extractor_device_points(cs_extractor *ex);
 /* After a submit_host + wait: pointer to the pinned host records. */
 void *cs_extractor_host_points(cs_extractor *ex);
