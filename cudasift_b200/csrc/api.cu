@@ -727,6 +727,7 @@ int cs_set_tuning(const char *key, int value)
   if (key && strcmp(key, "detect_variant") == 0) { cs::g_detect_variant = value; return 0; }
   if (key && strcmp(key, "detect_skip") == 0) { cs::g_detect_skip = value; return 0; }
   if (key && strcmp(key, "legacy") == 0) { cs::g_legacy = value ? 1 : 0; return 0; }
+  if (key && strcmp(key, "d2_variant") == 0) { cs::g_d2_variant = value; return 0; }
   if (key && strcmp(key, "d2_hs") == 0) { cs::g_d2_hs = value; return 0; }
   if (key && strcmp(key, "pa_rows") == 0) { cs::g_pa_rows = value; return 0; }
   if (key && strcmp(key, "cap32") == 0) { cs::g_cap32 = value ? 1 : 0; return 0; }

@@ -152,7 +152,8 @@ __device__ __forceinline__ void d2_refine(const float (&v)[3][3][3], int gx, int
   else d2_store_keypoint(pts, maxPts, atomicAdd(counter, 1u), kp);
 }
 
-__global__ void __launch_bounds__(D2_THREADS, 2)
+template <int MINB>
+__global__ void __launch_bounds__(D2_THREADS, MINB)
 detect2_kernel(const __grid_constant__ Detect2Params P)
 {
   extern __shared__ __align__(128) unsigned char d2_smem[];
@@ -399,7 +400,371 @@ detect2_kernel(const __grid_constant__ Detect2Params P)
   }
 }
 
+// ================================================================================================
+// detect3: the same marching detector, warp-specialised.  One CTA of 16 warps per SM:
+//   warps 12-15 (producers): vertical pass of all 8 scales (thread = columns c and c+128, 9-row register
+//                           window, 40 taps in registers) and the TMA row ring -- the serial critical path, kept short
+//   warps 0-3 / 4-7 / 8-11 (consumer groups 0 / 1 / 2): horizontal pass + DoG + candidate flags of the steps
+//                           k = g mod 3 (2 x 16 column groups), then the extrema tests of row k-4; each group has
+//                           three steps of time for one step of work
+// The producers run ahead of the consumers through three vertical-result buffers (buffer = group); hand-over is by
+// named barriers (bar.arrive / bar.sync) instead of CTA-wide barriers:
+//   FULL[g]  producers -> group g: v[g] written        EMPTY[g] group g -> producers: v[g] is in registers
+//   DONE[g]  group g -> producers: its step (DoG row, candidate list, extrema tests) is complete; the producers check
+//            it three steps later, just before they signal FULL of the group's next step.  Hence, when a group
+//            passes FULL of step k, every step <= k-3 of every group is complete: it may test the extrema of row k-4
+//            (rows k-5..k-3) and overwrite ring slot k mod 8 (last read for row k-7).
+// ================================================================================================
+#define D3_THREADS 512
+#define D3_PT 128
+#define D3_RS 8
+#define D3_SMEM_RING (D3_RS * D2_RSLOTF * 4)            // 112000
+#define D3_SMEM_LIST (D3_RS * 512 * 2)                  // 8192
+#define D3_NB 3                                          // vertical-result buffers
+#define D3_SMEM_V (D3_NB * D2_VBUF2 * 8)                // 49536
+#define D3_SMEM_BYTES (D2_SMEM_IN + D3_SMEM_V + D3_SMEM_RING + D3_SMEM_LIST)   // 186112
+
+__device__ __forceinline__ void nb_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+#define NB_FULL 1      // + group (3)
+#define NB_EMPTY 4     // + group (3)
+#define NB_DONE 7      // + group (3)
+#define NB_PINT 10
+
+struct D3Item {
+  int level, img, x0, ry0, hs, w, h;
+  float thresh, subsampling, lowestScale, edgeLimit, factor;
+  SiftPoint *pts;
+  unsigned int *counters;
+  int maxPts;
+  unsigned int *cells, *ovf;
+  int cellBase, cellsX;
+};
+
+// Extrema of step j (DoG rows ry0-1+j / ry0+hs-1+j) by the 128 producer threads; rows j-1, j, j+1 are complete.
+__device__ __noinline__ void d3_extrema(const D3Item &I, int j, int pt, const float *s_ring, const unsigned short *s_list,
+                                        const int *s_cnt, D2Keypoint *s_kq, int *s_kn)
+{
+  const int qj = j & (D3_RS - 1);
+  int n = s_cnt[qj];
+  if (n == 0) return;
+  const bool scan = n > D2_LCAP;                    // list overflow: test every pixel of the row pair
+  if (scan) n = 2 * CS_NUM_SCALES * D2_TESTED;
+  const float *rm = s_ring + ((j + D3_RS - 1) & (D3_RS - 1)) * D2_RSLOTF, *r0 = s_ring + qj * D2_RSLOTF,
+              *rp = s_ring + ((j + 1) & (D3_RS - 1)) * D2_RSLOTF;
+  for (int i = pt; i < n; i += D3_PT) {
+    int dc, p, hf;
+    if (!scan) {
+      const int e = s_list[qj * 512 + i];
+      dc = e & 255; p = (e >> 8) & 7; hf = e >> 11;
+    } else {
+      hf = i / (CS_NUM_SCALES * D2_TESTED);
+      const int r = i - hf * (CS_NUM_SCALES * D2_TESTED);
+      p = r / D2_TESTED;
+      dc = 1 + r - p * D2_TESTED;
+      p += 1;
+      const int gy_ = (hf ? I.ry0 + I.hs - 1 : I.ry0 - 1) + j;
+      if (gy_ > I.h - 2 || I.x0 + dc > I.w - 2) continue;
+    }
+    const int o = p * D2_RROWF + 2 * dc + hf;
+    const float c = r0[o];
+    if (!(fabsf(c) > I.thresh)) continue;
+    float v[3][3][3];
+#pragma unroll
+    for (int pp = 0; pp < 3; pp++)
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++) {
+        const int oo = o + (pp - 1) * D2_RROWF + 2 * (dx - 1);
+        v[pp][0][dx] = rm[oo];
+        v[pp][1][dx] = r0[oo];
+        v[pp][2][dx] = rp[oo];
+      }
+    bool mx = true, mn = true;
+#pragma unroll
+    for (int pp = 0; pp < 3; pp++)
+#pragma unroll
+      for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 3; dx++)
+          if (pp != 1 || dy != 1 || dx != 1) { mx = mx && (c > v[pp][dy][dx]); mn = mn && (c < v[pp][dy][dx]); }
+    if (c > 0.0f ? mx : mn) {
+      const int gx = I.x0 + dc, gy = (hf ? I.ry0 + I.hs - 1 : I.ry0 - 1) + j;
+      const unsigned int tag = (unsigned)gx | ((unsigned)gy << 13) | ((unsigned)(p - 1) << 26) | ((unsigned)I.level << 29);
+      if (I.cells) {                                // extrema per 30x8 block and scale (reference cap, cudaSiftD.cu:1371)
+        const int cell = I.cellBase + ((gy >> 3) * I.cellsX + gx / 30) * CS_NUM_SCALES + (p - 1);
+        unsigned int *cw = I.cells + (cell >> 2);
+        const unsigned old = atomicAdd(cw, 1u << (8 * (cell & 3)));
+        if (((old >> (8 * (cell & 3))) & 0xff) == 32) {      // the 33rd extremum of this cell
+          const unsigned at = atomicAdd(&I.counters[3], 1u);
+          if (at < CS_OVF_MAX) I.ovf[at] = (unsigned)cell;
+        }
+      }
+      d2_refine(v, gx, gy, p - 1, I.subsampling, I.lowestScale, I.edgeLimit, I.factor, tag, s_kq, s_kn, I.pts,
+                &I.counters[0], I.maxPts);
+    }
+  }
+}
+
+// vertical pass of one step, all 8 scales of both columns
+template <int PH>
+__device__ __forceinline__ void d3_vertical(f32x2 (&W0)[9], f32x2 (&W1)[9], f32x2 n0, f32x2 n1,
+                                            const float (&kv)[CS_LAPLACE_S][5], float2 *vdst)
+{
+#define D3_WI(i) ((PH + 1 + (i)) % 9)
+  W0[PH] = n0;
+  W1[PH] = n1;
+  {
+    const f32x2 c = W0[D3_WI(4)];
+    const f32x2 p1 = add2(W0[D3_WI(3)], W0[D3_WI(5)]), p2 = add2(W0[D3_WI(2)], W0[D3_WI(6)]);
+    const f32x2 p3 = add2(W0[D3_WI(1)], W0[D3_WI(7)]), p4 = add2(W0[D3_WI(0)], W0[D3_WI(8)]);
+#pragma unroll
+    for (int s = 0; s < CS_LAPLACE_S; s++) vdst[s * D2_VROW2] = upk(d2_sym9(kv[s], c, p1, p2, p3, p4));
+  }
+  {
+    const f32x2 c = W1[D3_WI(4)];
+    const f32x2 p1 = add2(W1[D3_WI(3)], W1[D3_WI(5)]), p2 = add2(W1[D3_WI(2)], W1[D3_WI(6)]);
+    const f32x2 p3 = add2(W1[D3_WI(1)], W1[D3_WI(7)]), p4 = add2(W1[D3_WI(0)], W1[D3_WI(8)]);
+#pragma unroll
+    for (int s = 0; s < CS_LAPLACE_S; s++) vdst[s * D2_VROW2 + 128] = upk(d2_sym9(kv[s], c, p1, p2, p3, p4));
+  }
+#undef D3_WI
+}
+
+__global__ void __launch_bounds__(D3_THREADS, 1)
+detect3_kernel(const __grid_constant__ Detect2Params P)
+{
+  extern __shared__ __align__(128) unsigned char d2_smem[];
+  float *s_in = reinterpret_cast<float *>(d2_smem);                                         // [slot][stream][256]
+  float2 *s_v = reinterpret_cast<float2 *>(d2_smem + D2_SMEM_IN);                           // [buf][scale][258]
+  float *s_ring = reinterpret_cast<float *>(d2_smem + D2_SMEM_IN + D3_SMEM_V);              // [slot][plane][500]
+  unsigned short *s_list = reinterpret_cast<unsigned short *>(d2_smem + D2_SMEM_IN + D3_SMEM_V + D3_SMEM_RING);
+  __shared__ __align__(8) uint64_t s_full[D2_NS];
+  __shared__ int s_cnt[D3_RS];
+  __shared__ int s_kn, s_next;
+  __shared__ D2Keypoint s_kq[D2_KQ];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = warp >= 12;       // the highest warp ids: the issue arbiter favours them, and they are the critical path
+  const int pt = tid - 384;               // producer thread index (0..127)
+
+  int item = blockIdx.x;
+  unsigned int req = 0;
+  if (tid == 0) req = gridDim.x + atomicAdd(P.sched, 1u);
+
+  while (item < P.numItems) {
+    const uint4 it = __ldg(P.items + item);
+    const int level = it.x & 0xff, img = it.x >> 8;
+    const int x0 = (int)it.y, ry0 = (int)it.z, hs = (int)it.w;
+    const D2Level &L = P.lev[level];
+    const int w = L.w, h = L.h;
+    const int nsteps = hs + 2;                            // DoG rows ry0-1+k (stream A), ry0+hs-1+k (stream B), k < nsteps
+    const int nrows = 8 + nsteps;                         // input rows per stream: ry0-5+i (A), i < nrows
+
+    __syncthreads();     // previous item complete (extrema, keypoint flush)
+    if (tid == 0) {
+      for (int i = 0; i < D2_NS; i++) mbarrier_init(&s_full[i], 1);
+      mbarrier_init_fence();
+      for (int i = 0; i < D3_RS; i++) s_cnt[i] = 0;
+      s_kn = 0;
+      s_next = (int)req;                                  // requested during the previous item
+      req = gridDim.x + atomicAdd(P.sched, 1u);
+    }
+    __syncthreads();
+
+    if (producer) {
+      // ================================================================== producers
+      const CUtensorMap *map = P.maps + (size_t)img * CS_MAX_LEVELS + level;
+      if (pt == 0) {
+        tensormap_acquire(map);
+        for (int i = 0; i < D2_NS; i++) {                 // prologue rows: all in flight at once
+          mbarrier_expect_tx(&s_full[i], 2 * D2_IW * 4);
+          tma_load_2d(s_in + (2 * i) * D2_IW, map, x0 - 4, min(max(ry0 - 5 + i, 0), h - 1), &s_full[i]);
+          tma_load_2d(s_in + (2 * i + 1) * D2_IW, map, x0 - 4, min(max(ry0 + hs - 5 + i, 0), h - 1), &s_full[i]);
+        }
+      }
+      // columns this thread reads from a staged row (clamped to the image: cudaSiftD.cu:1764-1767)
+      const int ci0 = min(max(x0 - 4 + pt, 0), w - 1) - (x0 - 4);
+      const int ci1 = min(max(x0 - 4 + pt + 128, 0), w - 1) - (x0 - 4);
+      float kv[CS_LAPLACE_S][5];
+#pragma unroll
+      for (int s = 0; s < CS_LAPLACE_S; s++)
+#pragma unroll
+        for (int j = 0; j < 5; j++) kv[s][j] = L.taps.k[s][j];
+      f32x2 W0[9], W1[9];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        mbarrier_wait(&s_full[i], 0);
+        const float *ra = s_in + (2 * i) * D2_IW, *rb = ra + D2_IW;
+        W0[i] = pk2(ra[ci0], rb[ci0]);
+        W1[i] = pk2(ra[ci1], rb[ci1]);
+      }
+      W0[8] = 0ull; W1[8] = 0ull;
+      nb_sync(NB_PINT, D3_PT);                            // every producer has read the prologue rows
+      if (pt == 0) {
+        for (int i = 0; i < D2_NS; i++)
+          if (8 + i < nrows) {
+            mbarrier_expect_tx(&s_full[i], 2 * D2_IW * 4);
+            tma_load_2d(s_in + (2 * i) * D2_IW, map, x0 - 4, min(max(ry0 + 3 + i, 0), h - 1), &s_full[i]);
+            tma_load_2d(s_in + (2 * i + 1) * D2_IW, map, x0 - 4, min(max(ry0 + hs + 3 + i, 0), h - 1), &s_full[i]);
+          }
+      }
+      // rows of step 0 (software pipelining: the rows of step m+1 are fetched at the end of step m)
+      f32x2 n0, n1;
+      {
+        mbarrier_wait(&s_full[0], 1);
+        n0 = pk2(s_in[ci0], s_in[D2_IW + ci0]);
+        n1 = pk2(s_in[ci1], s_in[D2_IW + ci1]);
+      }
+      // step m: window slot of the newest row = (8 + m) % 9 -> unrolled by 9 so that the slots are compile-time.
+      // The EMPTY hand-over (all 128 producers take part) doubles as the producers' own barrier: past it, every
+      // producer has finished step m-1, so the input slots read up to then may be refilled.
+#define D3_PSTEP(p)                                                                                           \
+  {                                                                                                           \
+    const int m = m0 + (p);                                                                                   \
+    if (m >= nsteps + 3) break;                                                                               \
+    f32x2 x0n = 0ull, x1n = 0ull;                                                                             \
+    if (m < nsteps) {                                                                                         \
+      if (m >= D3_NB) nb_sync(NB_EMPTY + (p) % D3_NB, 2 * D3_PT);                                             \
+      if (m + 1 < nsteps) {                  /* rows of step m+1: their latency hides behind this step's math */ \
+        const int slot = (m + 1) & (D2_NS - 1);                                                               \
+        mbarrier_wait(&s_full[slot], ((9 + m) >> 3) & 1);                                                     \
+        const float *ra = s_in + (2 * slot) * D2_IW, *rb = ra + D2_IW;                                        \
+        x0n = pk2(ra[ci0], rb[ci0]);                                                                          \
+        x1n = pk2(ra[ci1], rb[ci1]);                                                                          \
+      }                                                                                                       \
+      d3_vertical<(8 + (p)) % 9>(W0, W1, n0, n1, kv, s_v + ((p) % D3_NB) * D2_VBUF2 + pt);                    \
+      n0 = x0n; n1 = x1n;                                                                                     \
+    }                                                                                                         \
+    /* the group's previous step (m-3, with the extrema of row m-7) is complete */                            \
+    if (m >= D3_NB) nb_sync(NB_DONE + (p) % D3_NB, 2 * D3_PT);                                                \
+    if (pt == 0 && m >= 7) s_cnt[(m - 7) & (D3_RS - 1)] = 0;     /* list of row m-7: next used at step m+1 */   \
+    nb_arrive(NB_FULL + (p) % D3_NB, 2 * D3_PT);               /* in the drain steps: only releases the tests */ \
+    if (pt == 0 && m >= D3_NB && m < nsteps) {                                                                \
+      /* past EMPTY of this step every producer has finished step m-1: refill the slots read up to then */     \
+      for (int r = (m == D3_NB ? 0 : m - 1); r < m; r++)                                                      \
+        if (16 + r < nrows) {                                                                                 \
+          const int rs = r & (D2_NS - 1);                                                                     \
+          mbarrier_expect_tx(&s_full[rs], 2 * D2_IW * 4);                                                     \
+          tma_load_2d(s_in + (2 * rs) * D2_IW, map, x0 - 4, min(max(ry0 + 11 + r, 0), h - 1), &s_full[rs]);     \
+          tma_load_2d(s_in + (2 * rs + 1) * D2_IW, map, x0 - 4, min(max(ry0 + hs + 11 + r, 0), h - 1), &s_full[rs]); \
+        }                                                                                                     \
+    }                                                                                                         \
+  }
+      for (int m0 = 0;; m0 += 9) {
+        D3_PSTEP(0) D3_PSTEP(1) D3_PSTEP(2) D3_PSTEP(3) D3_PSTEP(4) D3_PSTEP(5) D3_PSTEP(6) D3_PSTEP(7) D3_PSTEP(8)
+      }
+#undef D3_PSTEP
+    } else {
+      // ================================================================== consumers
+      // No divergence in here: lanes whose 8 columns lie outside the strip or the image compute on whatever the
+      // buffer holds (in-bounds garbage) and only their stores and candidate flags are masked, so the shuffles
+      // run with the full mask and every shared address is (per-thread constant) + (per-step constant).
+      const int g = warp >> 2, wg = warp & 3;                   // group g: steps k = g mod 3, buffer g
+      const int hs_ = lane & 7, cgl = lane >> 3;                // scale, column group within the warp
+      const float thresh = P.thresh;
+      float kh[5];
+#pragma unroll
+      for (int j = 0; j < 5; j++) kh[j] = L.taps.k[hs_][j];
+      const float4 *vsrc0 = reinterpret_cast<const float4 *>(s_v + g * D2_VBUF2 + hs_ * D2_VROW2 + 8 * (4 * wg + cgl));
+      float *rdst0 = s_ring + max(hs_ - 1, 0) * D2_RROWF + 16 * (4 * wg + cgl);
+      D3Item I;
+      I.level = level; I.img = img; I.x0 = x0; I.ry0 = ry0; I.hs = hs; I.w = w; I.h = h;
+      I.thresh = P.thresh; I.subsampling = L.subsampling; I.lowestScale = L.lowestScale;
+      I.edgeLimit = P.edgeLimit; I.factor = P.factor;
+      I.pts = P.pts + (size_t)img * P.ptsStride;
+      I.counters = P.counters + (size_t)img * CS_CNT_STRIDE;
+      I.maxPts = P.maxPts;
+      I.cells = P.cells ? P.cells + (size_t)img * P.cellWords : nullptr;
+      I.ovf = P.ovf ? P.ovf + (size_t)img * CS_OVF_MAX : nullptr;
+      I.cellBase = P.cellBase[level]; I.cellsX = P.cellsX[level];
+      const bool testable = hs_ >= 2 && hs_ <= 6;               // DoG planes 1..5
+      const int tig = tid & 127;                                // thread index within the group
+      for (int k = g; k < nsteps + 3; k += D3_NB) {
+        const int q = k & (D3_RS - 1);
+        if (k >= nsteps) {                                      // drain: only the extrema of the last rows
+          nb_sync(NB_FULL + g, 2 * D3_PT);
+          if (k - 4 <= hs) d3_extrema(I, k - 4, tig, s_ring, s_list, s_cnt, s_kq, &s_kn);
+          continue;
+        }
+        const bool rowsTested = testable && k >= 1 && k <= hs;
+        const bool okA = ry0 - 1 + k <= h - 2, okB = ry0 + hs - 1 + k <= h - 2;
+        nb_sync(NB_FULL + g, 2 * D3_PT);
+#pragma unroll
+        for (int pass = 0; pass < 2; pass++) {
+          const int cg = 16 * pass + 4 * wg + cgl;
+          const bool act = cg < 31 && x0 + 8 * cg <= w - 1;      // this lane's 8 DoG columns start inside the image
+          const float4 *src = vsrc0 + 64 * pass;                 // 16 column groups further = 128 pairs
+          f32x2 V[16];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float4 t4 = src[j];
+            V[2 * j] = pk2(t4.x, t4.y);
+            V[2 * j + 1] = pk2(t4.z, t4.w);
+          }
+          if (pass == 1 && k + D3_NB < nsteps) nb_arrive(NB_EMPTY + g, 2 * D3_PT);   // v[g] is in registers
+          f32x2 dg[8];
+#pragma unroll
+          for (int d = 0; d < 8; d++) {
+            const f32x2 o = d2_sym9(kh, V[d + 4], add2(V[d + 3], V[d + 5]), add2(V[d + 2], V[d + 6]),
+                                    add2(V[d + 1], V[d + 7]), add2(V[d], V[d + 8]));
+            const float2 of = upk(o);
+            const float plo = __shfl_up_sync(0xffffffffu, of.x, 1), phi = __shfl_up_sync(0xffffffffu, of.y, 1);
+            dg[d] = sub2(o, pk2(plo, phi));                 // blur[s] - blur[s-1]: DoG plane s-1 (cudaSiftD.cu:1790)
+          }
+          if (act && hs_ >= 1) {
+            float4 *dst = reinterpret_cast<float4 *>(rdst0 + q * D2_RSLOTF + 256 * pass);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const float2 a = upk(dg[2 * j]), b = upk(dg[2 * j + 1]);
+              dst[j] = make_float4(a.x, a.y, b.x, b.y);
+            }
+          }
+          float m = 0.0f;
+#pragma unroll
+          for (int d = 0; d < 8; d++) {
+            const float2 a = upk(dg[d]);
+            m = fmaxf(m, fmaxf(fabsf(a.x), fabsf(a.y)));
+          }
+          if (m > thresh && rowsTested && act) {
+            unsigned bits = 0, colok = 0;
+#pragma unroll
+            for (int d = 0; d < 8; d++) {
+              const float2 a = upk(dg[d]);
+              const int dc = 8 * cg + d;
+              if (dc >= 1 && dc <= D2_TESTED && x0 + dc <= w - 2) colok |= 0x101u << d;
+              if (okA && fabsf(a.x) > thresh) bits |= 1u << d;
+              if (okB && fabsf(a.y) > thresh) bits |= 0x100u << d;
+            }
+            bits &= colok;
+            if (bits) {
+              int at = atomicAdd(&s_cnt[q], __popc(bits));
+              while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (at < D2_LCAP) s_list[q * 512 + at] = (unsigned short)((8 * cg + (b & 7)) | ((hs_ - 1) << 8) | ((b >> 3) << 11));
+                at++;
+              }
+            }
+          }
+        }
+        if (k >= 5) d3_extrema(I, k - 4, tig, s_ring, s_list, s_cnt, s_kq, &s_kn);   // rows k-5..k-3 are complete
+        nb_arrive(NB_DONE + g, 2 * D3_PT);
+      }
+    }
+    __syncthreads();
+    {
+      const int nkq = min(s_kn, D2_KQ);
+      if (tid < nkq)
+        d2_store_keypoint(P.pts + (size_t)img * P.ptsStride, P.maxPts,
+                          atomicAdd(&P.counters[(size_t)img * CS_CNT_STRIDE], 1u), s_kq[tid]);
+    }
+    item = s_next;
+  }
+}
+
+
 static int g_d2_configured[64];
+int g_d2_variant = 2;     // tuning: 2 = warp-specialised detect3 (default); 0 / 1 = detect2 with 2 / 1 CTAs per SM
 
 int launch_detect2(const Detect2Params &p, int sms, cudaStream_t st)
 {
@@ -407,11 +772,22 @@ int launch_detect2(const Detect2Params &p, int sms, cudaStream_t st)
   int dev = 0;
   CS_CUDA(cudaGetDevice(&dev));
   if (dev < 64 && !g_d2_configured[dev]) {      // per device: cudaFuncSetAttribute applies to the current device only
-    CS_CUDA(cudaFuncSetAttribute(detect2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BYTES));
+    CS_CUDA(cudaFuncSetAttribute(detect2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BYTES));
+    CS_CUDA(cudaFuncSetAttribute(detect2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, D2_SMEM_BYTES));
+    CS_CUDA(cudaFuncSetAttribute(detect3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, D3_SMEM_BYTES));
     g_d2_configured[dev] = 1;
   }
-  const int grid = p.numItems < 2 * sms ? p.numItems : 2 * sms;
-  detect2_kernel<<<grid, D2_THREADS, D2_SMEM_BYTES, st>>>(p);
+  if (g_d2_variant == 2) {
+    const int grid3 = p.numItems < sms ? p.numItems : sms;
+    detect3_kernel<<<grid3, D3_THREADS, D3_SMEM_BYTES, st>>>(p);
+    count_launch();
+    CS_CUDA(cudaGetLastError());
+    return 0;
+  }
+  const int per = g_d2_variant == 1 ? 1 : 2;
+  const int grid = p.numItems < per * sms ? p.numItems : per * sms;
+  if (g_d2_variant == 1) detect2_kernel<1><<<grid, D2_THREADS, D2_SMEM_BYTES, st>>>(p);
+  else detect2_kernel<2><<<grid, D2_THREADS, D2_SMEM_BYTES, st>>>(p);
   count_launch();
   CS_CUDA(cudaGetLastError());
   return 0;

@@ -43,6 +43,6 @@ struct Pipeline2 {
               PyrAParams *paOut = nullptr);
 };
 
-extern int g_d2_hs, g_pa_rows, g_cap32;
+extern int g_d2_hs, g_pa_rows, g_cap32, g_d2_variant;
 
 }  // namespace cs
