@@ -44,9 +44,11 @@ describe_kernel(const __grid_constant__ DescribeParams P)
   __shared__ float s_gauss16[16];
   __shared__ float s_ow[121];          // orientation sample weights
   __shared__ int s_obin[121];          // orientation sample bins
-  __shared__ __align__(16) float s_g2[256][4];   // descriptor votes per sample: ul, ll, ur, lr
-  __shared__ float s_angf[256];
-  __shared__ int s_angi[256];
+  // per-sample tables of the descriptor stage, row stride 17 (the accumulation reads them down the rows:
+  // stride 16 would put every other row on the same bank)
+  __shared__ float s_g2[4][16 * 17];             // descriptor votes per sample: ul, ll, ur, lr
+  __shared__ float s_angf[16 * 17];
+  __shared__ int s_angi[16 * 17];
   __shared__ float s_hp[32][33];       // orientation: private 32-bin histograms of warp 0's lanes
   __shared__ float s_pb[128][9];       // descriptor: private angle bins (+ Q22 overflow slot) per (cell, row)
   __shared__ float s_sums[4];
@@ -196,10 +198,13 @@ describe_kernel(const __grid_constant__ DescribeParams P)
         // the reference then adds its "iangf" vote at flat index 8*cell + 8, i.e. into angle
         // bin 0 of the NEXT cell (cudaSiftD.cu:353-384).  Reproduced in the accumulation below.
         float gl = __fmul_rn(ihorf, grad), gr = __fmul_rn(horf, grad);
-        float4 g2 = make_float4(__fmul_rn(iverf, gl), __fmul_rn(verf, gl), __fmul_rn(iverf, gr), __fmul_rn(verf, gr));
-        *reinterpret_cast<float4 *>(s_g2[sidx]) = g2;
-        s_angf[sidx] = angf;
-        s_angi[sidx] = angi;
+        const int pidx = y * 17 + x;
+        s_g2[0][pidx] = __fmul_rn(iverf, gl);
+        s_g2[1][pidx] = __fmul_rn(verf, gl);
+        s_g2[2][pidx] = __fmul_rn(iverf, gr);
+        s_g2[3][pidx] = __fmul_rn(verf, gr);
+        s_angf[pidx] = angf;
+        s_angi[pidx] = angi;
       }
       __syncthreads();
       {  // deterministic accumulation.  Thread (cell, k): the k-th sample row of the cell's 8x8
@@ -216,11 +221,11 @@ describe_kernel(const __grid_constant__ DescribeParams P)
           const int xlo = max(0, 4 * cx - 2), xhi = min(15, 4 * cx + 5);
           for (int x = xlo; x <= xhi; x++) {
             const int right = (((x + 2) >> 2) - 1 != cx);     // ... into its right cell
-            const int sidx = y * 16 + x;
+            const int sidx = y * 17 + x;
             const int angi = s_angi[sidx];
             const int angp = (angi < 7 ? angi + 1 : 0);
             const float af = s_angf[sidx];
-            const float g2 = s_g2[sidx][2 * right + lower];
+            const float g2 = s_g2[2 * right + lower][sidx];
             const int a1 = min(angi, 8);
             pb[a1] = __fadd_rn(pb[a1], __fmul_rn(__fsub_rn(1.0f, af), g2));
             pb[angp] = __fadd_rn(pb[angp], __fmul_rn(af, g2));

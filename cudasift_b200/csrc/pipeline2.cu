@@ -293,7 +293,7 @@ int Pipeline2::enqueue(int n, const float *const *d_imgs, int pitch, double init
     dp.lev0Img[i] = arena + levOff[i]; dp.levPitch[i] = lp[i];
   }
   dp.imgStride = (long long)perImage;
-  const int hs = g_d2_hs > 0 ? g_d2_hs : (n >= 4 ? 32 : 16);
+  const int hs = g_d2_hs > 0 ? g_d2_hs : (n >= 8 ? 64 : (n >= 2 ? 32 : 16));
   if ((r = get_items(n, hs, &dp.items, &dp.numItems)) < 0) return r;
   dp.maps = d_maps;
   dp.thresh = thresh; dp.edgeLimit = 10.0f; dp.factor = 1.0f / CS_NUM_SCALES;   // cudaSiftH.cu:213

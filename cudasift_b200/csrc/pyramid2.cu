@@ -50,31 +50,136 @@ __device__ __forceinline__ float sd_v(const Taps5 &t, float r0, float r1, float 
 #define PA_THREADS 64
 #define PA_IW 256          // staged input columns: x0-8 .. x0+247
 #define PA_NS 8            // input rows in flight per CTA
-#define PA_HR 16           // rows of horizontally filtered history per thread
+
+// One marching step.  PH: window slot that receives the horizontally filtered row u (compile-time: the step loop
+// is unrolled by 9).  The 9-row window of horizontally filtered rows lives in registers (one float4 per row).
+struct PaCtx {
+  int w, h, x0, R0, R1, ya, yb, ia, ib, Y1b, p0, p1, w1, cb, x1;
+  bool edge, act, own, sd;
+  float *lev0, *lev1;
+};
+
+template <int PH>
+__device__ __forceinline__ void pa_step(const PaCtx &C, int u, int &nextY1, float4 (&W)[9], const Taps9 &lp, const Taps5 &sdk,
+                                        float (*s_in)[PA_IW], float (*s_l0)[PA_IW], float2 (*s_h2)[PA_THREADS],
+                                        uint64_t *s_full, const CUtensorMap *map)
+{
+  const int t = threadIdx.x;
+  if (u <= C.ib) {
+    // ---------------------------------------------------------------- horizontal 9-tap of input row u
+    const int seq = u - C.ia, slot = seq & (PA_NS - 1);
+    mbarrier_wait(&s_full[slot], (seq >> 3) & 1);
+    if (C.act) {
+      float v[12];
+      if (!C.edge) {
+        const float4 *p = reinterpret_cast<const float4 *>(&s_in[slot][4 * t]);
+        const float4 a = p[0], b = p[1], c = p[2];
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 12; i++) v[i] = s_in[slot][clampi2(C.cb - 4 + i, 0, C.w - 1) - (C.x0 - 8)];
+      }
+      float o[4];
+#pragma unroll
+      for (int d = 0; d < 4; d++)
+        o[d] = pa_sym9(lp, v[d + 4], __fadd_rn(v[d + 5], v[d + 3]), __fadd_rn(v[d + 6], v[d + 2]),
+                       __fadd_rn(v[d + 7], v[d + 1]), __fadd_rn(v[d + 8], v[d]));
+      W[PH] = make_float4(o[0], o[1], o[2], o[3]);
+      if (u == 0) {                         // rows above the image are row 0 (cudaSiftD.cu:1997 clamps the row index)
+#pragma unroll
+        for (int i = 0; i < 9; i++) W[i] = W[PH];
+      }
+    }
+  } else if (C.act) {
+    W[PH] = W[(PH + 8) % 9];                // rows below the image are row h-1
+  }
+  const int y = u - 4;
+  const bool row = y >= C.ya && y <= C.yb;
+  if (row && C.act) {
+    // ------------------------------------------------------------------ vertical 9-tap -> level-0 row y
+    // window order: oldest = slot PH+1 (row y-4) ... newest = slot PH (row y+4)
+#define PAW(i) W[(PH + 1 + (i)) % 9]
+    float4 o;
+#define PAV(f) pa_sym9(lp, PAW(4).f, __fadd_rn(PAW(3).f, PAW(5).f), __fadd_rn(PAW(2).f, PAW(6).f), __fadd_rn(PAW(1).f, PAW(7).f), __fadd_rn(PAW(0).f, PAW(8).f))
+    o.x = PAV(x); o.y = PAV(y); o.z = PAV(z); o.w = PAV(w);
+#undef PAV
+#undef PAW
+    if (C.own && y >= C.R0 && y < C.R1) {
+      float *out = C.lev0 + (size_t)y * C.p0 + C.cb;
+      if (C.cb + 3 < C.w) *reinterpret_cast<float4 *>(out) = o;
+      else {
+        if (C.cb < C.w) out[0] = o.x;
+        if (C.cb + 1 < C.w) out[1] = o.y;
+        if (C.cb + 2 < C.w) out[2] = o.z;
+      }
+    }
+    if (C.sd) *reinterpret_cast<float4 *>(&s_l0[y & 1][4 * t]) = o;
+  }
+  __syncthreads();
+  if (t == 0 && u + PA_NS <= C.ib) {                        // refill the slot of row u (u <= ib holds then)
+    const int slot = (u - C.ia) & (PA_NS - 1);
+    mbarrier_expect_tx(&s_full[slot], PA_IW * 4);
+    tma_load_2d(&s_in[slot][0], map, C.x0 - 8, u + PA_NS, &s_full[slot]);
+  }
+  if (C.sd && row) {
+    if (C.own) {
+      // ---------------------------------------------------------------- ScaleDown: horizontal 5-tap of row y
+      float a[7];
+      const float *l0 = s_l0[y & 1];
+      if (!C.edge) {                                        // columns cb-4 .. cb+7: three conflict-free 128-bit loads
+        const float4 *p = reinterpret_cast<const float4 *>(l0 + 4 * t - 4);
+        const float4 q0 = p[0], q1 = p[1], q2 = p[2];
+        a[0] = q0.z; a[1] = q0.w; a[2] = q1.x; a[3] = q1.y; a[4] = q1.z; a[5] = q1.w; a[6] = q2.x;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 7; i++) a[i] = l0[clampi2(C.cb - 2 + i, 0, C.w - 1) - (C.x0 - 4)];
+      }
+      s_h2[y & 7][t] = make_float2(sd_h(sdk, a[0], a[1], a[2], a[3], a[4]), sd_h(sdk, a[2], a[3], a[4], a[5], a[6]));
+    }
+    // ------------------------------------------------------------------ ... vertical 5-tap -> level-1 rows that are complete
+    while (nextY1 < C.Y1b && min(2 * nextY1 + 2, C.h - 1) <= y) {
+      if (C.own) {
+        float2 q[5];
+#pragma unroll
+        for (int j = 0; j < 5; j++) q[j] = s_h2[clampi2(2 * nextY1 - 2 + j, 0, C.h - 1) & 7][t];
+        const float ox = sd_v(sdk, q[0].x, q[1].x, q[2].x, q[3].x, q[4].x);
+        const float oy = sd_v(sdk, q[0].y, q[1].y, q[2].y, q[3].y, q[4].y);
+        float *out = C.lev1 + (size_t)nextY1 * C.p1 + C.x1;
+        if (C.x1 + 1 < C.w1) *reinterpret_cast<float2 *>(out) = make_float2(ox, oy);
+        else if (C.x1 < C.w1) out[0] = ox;
+      }
+      nextY1++;
+    }
+  }
+}
 
 __global__ void __launch_bounds__(PA_THREADS)
 pyr_lowpass_sd_kernel(const __grid_constant__ PyrAParams P)
 {
   __shared__ __align__(128) float s_in[PA_NS][PA_IW];
-  __shared__ __align__(16) float4 s_h[PA_HR][PA_THREADS];      // [row & 15][thread]: private columns
   __shared__ __align__(16) float s_l0[2][PA_IW];               // level-0 row handed to the ScaleDown
   __shared__ __align__(8) float2 s_h2[8][PA_THREADS];          // [row & 7][thread]: private columns
   __shared__ __align__(8) uint64_t s_full[PA_NS];
 
   const int t = threadIdx.x;
   const int strip = blockIdx.x % P.stripsX, rb = blockIdx.x / P.stripsX, img = blockIdx.y;
-  const int w = P.w, h = P.h;
-  const int x0 = strip * CS_PA_OWN;
-  const int R0 = rb * P.rowsPerCta, R1 = (rb == P.rowBlocks - 1) ? h : min(R0 + P.rowsPerCta, h);
-  const bool sd = P.lev1 != nullptr;
-  const int Y1a = R0 >> 1, Y1b = sd ? ((rb == P.rowBlocks - 1) ? P.h1 : min(R1 >> 1, P.h1)) : 0;
+  PaCtx C;
+  C.w = P.w; C.h = P.h;
+  C.x0 = strip * CS_PA_OWN;
+  C.R0 = rb * P.rowsPerCta;
+  C.R1 = (rb == P.rowBlocks - 1) ? C.h : min(C.R0 + P.rowsPerCta, C.h);
+  C.sd = P.lev1 != nullptr;
+  const int Y1a = C.R0 >> 1;
+  C.Y1b = C.sd ? ((rb == P.rowBlocks - 1) ? P.h1 : min(C.R1 >> 1, P.h1)) : 0;
   // level-0 rows this CTA computes / input rows it needs
-  const int ya = sd ? max(R0 - 2, 0) : R0;
-  const int yb = sd ? min(max(R1 - 1, 2 * Y1b), h - 1) : R1 - 1;
-  const int ia = max(ya - 4, 0), ib = min(yb + 4, h - 1);
+  C.ya = C.sd ? max(C.R0 - 2, 0) : C.R0;
+  C.yb = C.sd ? min(max(C.R1 - 1, 2 * C.Y1b), C.h - 1) : C.R1 - 1;
+  C.ia = max(C.ya - 4, 0); C.ib = min(C.yb + 4, C.h - 1);
+  C.p0 = P.p0; C.p1 = P.p1; C.w1 = P.w1;
   const CUtensorMap *map = P.inMaps + img;
-  float *lev0 = P.lev0 + (size_t)img * P.lev0Stride;
-  float *lev1 = sd ? P.lev1 + (size_t)img * P.lev1Stride : nullptr;
+  C.lev0 = P.lev0 + (size_t)img * P.lev0Stride;
+  C.lev1 = C.sd ? P.lev1 + (size_t)img * P.lev1Stride : nullptr;
 
   if (t == 0) {
     for (int i = 0; i < PA_NS; i++) mbarrier_init(&s_full[i], 1);
@@ -83,96 +188,29 @@ pyr_lowpass_sd_kernel(const __grid_constant__ PyrAParams P)
   __syncthreads();
   if (t == 0) {                                             // the maps are kernel parameters: no descriptor fence needed
     for (int i = 0; i < PA_NS; i++)
-      if (ia + i <= ib) {
+      if (C.ia + i <= C.ib) {
         mbarrier_expect_tx(&s_full[i], PA_IW * 4);
-        tma_load_2d(&s_in[i][0], map, x0 - 8, ia + i, &s_full[i]);
+        tma_load_2d(&s_in[i][0], map, C.x0 - 8, C.ia + i, &s_full[i]);
       }
   }
-
-  const bool edge = (x0 == 0) || (x0 + PA_IW - 8 > w);       // some staged column lies outside the image
-  const bool act = t < 62;                                   // level-0 columns cb .. cb+3
-  const int cb = x0 - 4 + 4 * t;
-  const bool own = t >= 1 && t <= 60;                        // owned columns x0 .. x0+239
-  const int x1 = (x0 >> 1) + 2 * (t - 1);                    // this thread's two level-1 columns
+  C.edge = (C.x0 == 0) || (C.x0 + PA_IW - 8 > C.w);        // some staged column lies outside the image
+  C.act = t < 62;                                           // level-0 columns cb .. cb+3
+  C.cb = C.x0 - 4 + 4 * t;
+  C.own = t >= 1 && t <= 60;                                // owned columns x0 .. x0+239
+  C.x1 = (C.x0 >> 1) + 2 * (t - 1);                         // this thread's two level-1 columns
   int nextY1 = Y1a;
+  const Taps9 lp = P.lp;
+  const Taps5 sdk = P.sd;
+  float4 W[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) W[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int u = ia; u <= yb + 4; u++) {
-    if (u <= ib) {
-      // ---------------------------------------------------------------- horizontal 9-tap of input row u
-      const int seq = u - ia, slot = seq & (PA_NS - 1);
-      mbarrier_wait(&s_full[slot], (seq >> 3) & 1);
-      if (act) {
-        float v[12];
-        if (!edge) {
-          const float4 *p = reinterpret_cast<const float4 *>(&s_in[slot][4 * t]);
-          const float4 a = p[0], b = p[1], c = p[2];
-          v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-          v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
-        } else {
-#pragma unroll
-          for (int i = 0; i < 12; i++) v[i] = s_in[slot][clampi2(cb - 4 + i, 0, w - 1) - (x0 - 8)];
-        }
-        float o[4];
-#pragma unroll
-        for (int d = 0; d < 4; d++)
-          o[d] = pa_sym9(P.lp, v[d + 4], __fadd_rn(v[d + 5], v[d + 3]), __fadd_rn(v[d + 6], v[d + 2]),
-                         __fadd_rn(v[d + 7], v[d + 1]), __fadd_rn(v[d + 8], v[d]));
-        s_h[u & (PA_HR - 1)][t] = make_float4(o[0], o[1], o[2], o[3]);
-      }
-    }
-    const int y = u - 4;
-    const bool row = y >= ya && y <= yb;
-    if (row && act) {
-      // ---------------------------------------------------------------- vertical 9-tap -> level-0 row y
-      float4 r[9];
-#pragma unroll
-      for (int j = 0; j < 9; j++) r[j] = s_h[clampi2(y - 4 + j, 0, h - 1) & (PA_HR - 1)][t];
-      float4 o;
-#define PAV(f) pa_sym9(P.lp, r[4].f, __fadd_rn(r[3].f, r[5].f), __fadd_rn(r[2].f, r[6].f), __fadd_rn(r[1].f, r[7].f), __fadd_rn(r[0].f, r[8].f))
-      o.x = PAV(x); o.y = PAV(y); o.z = PAV(z); o.w = PAV(w);
-#undef PAV
-      if (own && y >= R0 && y < R1) {
-        float *out = lev0 + (size_t)y * P.p0 + cb;
-        if (cb + 3 < w) *reinterpret_cast<float4 *>(out) = o;
-        else {
-          if (cb < w) out[0] = o.x;
-          if (cb + 1 < w) out[1] = o.y;
-          if (cb + 2 < w) out[2] = o.z;
-        }
-      }
-      if (sd) *reinterpret_cast<float4 *>(&s_l0[y & 1][4 * t]) = o;
-    }
-    __syncthreads();
-    if (t == 0 && u <= ib && u + PA_NS <= ib) {               // refill the slot of row u
-      const int slot = (u - ia) & (PA_NS - 1);
-      mbarrier_expect_tx(&s_full[slot], PA_IW * 4);
-      tma_load_2d(&s_in[slot][0], map, x0 - 8, u + PA_NS, &s_full[slot]);
-    }
-    if (sd && row && own) {
-      // ---------------------------------------------------------------- ScaleDown: horizontal 5-tap of row y
-      float a[7];
-      const float *l0 = s_l0[y & 1];
-#pragma unroll
-      for (int i = 0; i < 7; i++) a[i] = l0[clampi2(cb - 2 + i, 0, w - 1) - (x0 - 4)];
-      s_h2[y & 7][t] = make_float2(sd_h(P.sd, a[0], a[1], a[2], a[3], a[4]), sd_h(P.sd, a[2], a[3], a[4], a[5], a[6]));
-    }
-    if (sd && row) {
-      // ---------------------------------------------------------------- ... vertical 5-tap -> level-1 rows that are complete
-      while (nextY1 < Y1b && min(2 * nextY1 + 2, h - 1) <= y) {
-        if (own) {
-          float2 q[5];
-#pragma unroll
-          for (int j = 0; j < 5; j++) q[j] = s_h2[clampi2(2 * nextY1 - 2 + j, 0, h - 1) & 7][t];
-          const float ox = sd_v(P.sd, q[0].x, q[1].x, q[2].x, q[3].x, q[4].x);
-          const float oy = sd_v(P.sd, q[0].y, q[1].y, q[2].y, q[3].y, q[4].y);
-          float *out = lev1 + (size_t)nextY1 * P.p1 + x1;
-          if (x1 + 1 < P.w1) *reinterpret_cast<float2 *>(out) = make_float2(ox, oy);
-          else if (x1 < P.w1) out[0] = ox;
-        }
-        nextY1++;
-      }
-    }
+  const int uend = C.yb + 4;
+#define PA_STEP(p) { const int u = u0 + (p); if (u > uend) break; pa_step<(p)>(C, u, nextY1, W, lp, sdk, s_in, s_l0, s_h2, s_full, map); }
+  for (int u0 = C.ia;; u0 += 9) {
+    PA_STEP(0) PA_STEP(1) PA_STEP(2) PA_STEP(3) PA_STEP(4) PA_STEP(5) PA_STEP(6) PA_STEP(7) PA_STEP(8)
   }
+#undef PA_STEP
 }
 
 const void *pyr_a_func() { return (const void *)pyr_lowpass_sd_kernel; }
@@ -195,39 +233,91 @@ int launch_pyr_a(const PyrAParams &p, int batch, cudaStream_t st)
 #define PB_N2 (2 * PB_N1 + 3)     // 41
 #define PB_N3 (2 * PB_N2 + 3)     // 85
 
-// One ScaleDown inside shared memory.  src: nin x nin region of level `ls` whose element (0,0) is pixel
-// (sx0, sy0); dst: nout x nout region of the next level with origin (dx0, dy0) = ((sx0+2)/2, (sy0+2)/2).
-// Coordinates are clamped to the image first (cudaSiftD.cu:98-99,113), then to the region.
-__device__ __forceinline__ void pb_scaledown(const float *src, int nin, int sx0, int sy0, int sw, int sh,
-                                             float *tmp, float *dst, int nout, int dx0, int dy0, const Taps5 &k)
+// One ScaleDown inside shared memory.  src: NIN x NIN region of a level whose element (0,0) is pixel (sx0, sy0);
+// dst: NOUT x NOUT region of the next level with origin (dx0, dy0) = ((sx0+2)/2, (sy0+2)/2), NIN = 2 NOUT + 3.
+// CLAMP: coordinates are clamped to the image first (cudaSiftD.cu:98-99,113), then to the region; tiles whose
+// regions lie inside the images on every level take the CLAMP = false path (plain strided reads).
+template <int NOUT, bool CLAMP>
+__device__ __forceinline__ void pb_scaledown(const float *src, int sx0, int sy0, int sw, int sh, float *tmp, float *dst,
+                                             int dx0, int dy0, const Taps5 &k)
 {
-  for (int i = threadIdx.x; i < nin * nout; i += PB_THREADS) {      // horizontal: rows of src x columns of dst
-    const int r = i / nout, c = i - r * nout;
-    const float *row = src + r * nin;
+  constexpr int NIN = 2 * NOUT + 3;
+  for (int i = threadIdx.x; i < NIN * NOUT; i += PB_THREADS) {      // horizontal: rows of src x columns of dst
+    const int r = i / NOUT, c = i - r * NOUT;
+    const float *row = src + r * NIN;
     float a[5];
+    if (CLAMP) {
 #pragma unroll
-    for (int j = 0; j < 5; j++) a[j] = row[clampi2(clampi2(2 * (dx0 + c) - 2 + j, 0, sw - 1) - sx0, 0, nin - 1)];
-    tmp[r * nout + c] = sd_h(k, a[0], a[1], a[2], a[3], a[4]);
+      for (int j = 0; j < 5; j++) a[j] = row[clampi2(clampi2(2 * (dx0 + c) - 2 + j, 0, sw - 1) - sx0, 0, NIN - 1)];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 5; j++) a[j] = row[2 * c + j];
+    }
+    tmp[i] = sd_h(k, a[0], a[1], a[2], a[3], a[4]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < nout * nout; i += PB_THREADS) {
-    const int r = i / nout, c = i - r * nout;
+  for (int i = threadIdx.x; i < NOUT * NOUT; i += PB_THREADS) {
+    const int r = i / NOUT, c = i - r * NOUT;
     float q[5];
+    if (CLAMP) {
 #pragma unroll
-    for (int j = 0; j < 5; j++) q[j] = tmp[clampi2(clampi2(2 * (dy0 + r) - 2 + j, 0, sh - 1) - sy0, 0, nin - 1) * nout + c];
-    dst[r * nout + c] = sd_v(k, q[0], q[1], q[2], q[3], q[4]);
+      for (int j = 0; j < 5; j++) q[j] = tmp[clampi2(clampi2(2 * (dy0 + r) - 2 + j, 0, sh - 1) - sy0, 0, NIN - 1) * NOUT + c];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 5; j++) q[j] = tmp[(2 * r + j) * NOUT + c];
+    }
+    dst[i] = sd_v(k, q[0], q[1], q[2], q[3], q[4]);
   }
   __syncthreads();
 }
 
-// write the part of a region that this tile owns: pixels [ox, ox+on) x [oy, oy+on) of the level
-__device__ __forceinline__ void pb_store(const float *reg, int n, int rx0, int ry0, float *img, int w, int h, int pitch,
-                                         int ox, int oy, int on)
+// write the part of an N x N region (origin rx0, ry0) that this tile owns: pixels [ox, ox+ON) x [oy, oy+ON)
+template <int N, int ON>
+__device__ __forceinline__ void pb_store(const float *reg, int rx0, int ry0, float *img, int w, int h, int pitch, int ox, int oy)
 {
-  for (int i = threadIdx.x; i < on * on; i += PB_THREADS) {
-    const int r = i / on, c = i - r * on;
+  for (int i = threadIdx.x; i < ON * ON; i += PB_THREADS) {
+    const int r = i / ON, c = i - r * ON;
     const int gx = ox + c, gy = oy + r;
-    if (gx < w && gy < h) img[(size_t)gy * pitch + gx] = reg[(gy - ry0) * n + (gx - rx0)];
+    if (gx < w && gy < h) img[(size_t)gy * pitch + gx] = reg[(gy - ry0) * N + (gx - rx0)];
+  }
+}
+
+// chain of STEPS ScaleDowns for the 8x8 tile (bx, by) of the last level
+template <int STEPS, bool CLAMP>
+__device__ __forceinline__ void pb_chain(const PyrBParams &P, int img, float *bufA, float *bufT, float *bufB)
+{
+  constexpr int N0 = PB_T, N1 = 2 * N0 + 3, N2 = 2 * N1 + 3, N3 = 2 * N2 + 3;
+  constexpr int NS = STEPS == 3 ? N3 : (STEPS == 2 ? N2 : N1);          // source region
+  int ox[4], oy[4];
+  ox[0] = blockIdx.x * PB_T; oy[0] = blockIdx.y * PB_T;
+#pragma unroll
+  for (int k = 1; k <= 3; k++) { ox[k] = 2 * ox[k - 1] - 2; oy[k] = 2 * oy[k - 1] - 2; }
+  {
+    const float *src = P.img[0] + (size_t)img * P.stride[0];
+    const int sx0 = ox[STEPS], sy0 = oy[STEPS];
+    for (int i = threadIdx.x; i < NS * NS; i += PB_THREADS) {
+      const int r = i / NS, c = i - r * NS;
+      if (CLAMP) bufA[i] = __ldg(src + (size_t)clampi2(sy0 + r, 0, P.h[0] - 1) * P.pitch[0] + clampi2(sx0 + c, 0, P.w[0] - 1));
+      else bufA[i] = __ldg(src + (size_t)(sy0 + r) * P.pitch[0] + sx0 + c);
+    }
+  }
+  __syncthreads();
+  // level s is produced from region index STEPS-s+1 into region index STEPS-s
+  if (STEPS == 3) {
+    pb_scaledown<N2, CLAMP>(bufA, ox[3], oy[3], P.w[0], P.h[0], bufT, bufB, ox[2], oy[2], P.sd);
+    pb_store<N2, 4 * PB_T>(bufB, ox[2], oy[2], P.img[1] + (size_t)img * P.stride[1], P.w[1], P.h[1], P.pitch[1], 4 * ox[0], 4 * oy[0]);
+    pb_scaledown<N1, CLAMP>(bufB, ox[2], oy[2], P.w[1], P.h[1], bufT, bufA, ox[1], oy[1], P.sd);
+    pb_store<N1, 2 * PB_T>(bufA, ox[1], oy[1], P.img[2] + (size_t)img * P.stride[2], P.w[2], P.h[2], P.pitch[2], 2 * ox[0], 2 * oy[0]);
+    pb_scaledown<N0, CLAMP>(bufA, ox[1], oy[1], P.w[2], P.h[2], bufT, bufB, ox[0], oy[0], P.sd);
+    pb_store<N0, PB_T>(bufB, ox[0], oy[0], P.img[3] + (size_t)img * P.stride[3], P.w[3], P.h[3], P.pitch[3], ox[0], oy[0]);
+  } else if (STEPS == 2) {
+    pb_scaledown<N1, CLAMP>(bufA, ox[2], oy[2], P.w[0], P.h[0], bufT, bufB, ox[1], oy[1], P.sd);
+    pb_store<N1, 2 * PB_T>(bufB, ox[1], oy[1], P.img[1] + (size_t)img * P.stride[1], P.w[1], P.h[1], P.pitch[1], 2 * ox[0], 2 * oy[0]);
+    pb_scaledown<N0, CLAMP>(bufB, ox[1], oy[1], P.w[1], P.h[1], bufT, bufA, ox[0], oy[0], P.sd);
+    pb_store<N0, PB_T>(bufA, ox[0], oy[0], P.img[2] + (size_t)img * P.stride[2], P.w[2], P.h[2], P.pitch[2], ox[0], oy[0]);
+  } else {
+    pb_scaledown<N0, CLAMP>(bufA, ox[1], oy[1], P.w[0], P.h[0], bufT, bufB, ox[0], oy[0], P.sd);
+    pb_store<N0, PB_T>(bufB, ox[0], oy[0], P.img[1] + (size_t)img * P.stride[1], P.w[1], P.h[1], P.pitch[1], ox[0], oy[0]);
   }
 }
 
@@ -239,32 +329,18 @@ pyr_chain_kernel(const __grid_constant__ PyrBParams P)
   float *bufT = bufA + PB_N3 * PB_N3;          // horizontal results, up to 85 x 41
   float *bufB = bufT + PB_N3 * PB_N2;          // up to 41 x 41
   const int img = blockIdx.z;
-  const int steps = P.steps;                   // 1..3
-  // region sizes from the last level upwards: n[0] = 8 (last), n[k] = 2 n[k-1] + 3
-  int n[4], ox[4], oy[4];
-  n[0] = PB_T; ox[0] = blockIdx.x * PB_T; oy[0] = blockIdx.y * PB_T;
-  for (int k = 1; k <= steps; k++) { n[k] = 2 * n[k - 1] + 3; ox[k] = 2 * ox[k - 1] - 2; oy[k] = 2 * oy[k - 1] - 2; }
-  // stage the source region (level index 0 of P = the input of the chain), clamped
+  // the tile needs no clamping if its region lies inside the image on every level it reads
+  bool inside = true;
   {
-    const float *src = P.img[0] + (size_t)img * P.stride[0];
-    const int ns = n[steps], sx0 = ox[steps], sy0 = oy[steps];
-    for (int i = threadIdx.x; i < ns * ns; i += PB_THREADS) {
-      const int r = i / ns, c = i - r * ns;
-      bufA[i] = __ldg(src + (size_t)clampi2(sy0 + r, 0, P.h[0] - 1) * P.pitch[0] + clampi2(sx0 + c, 0, P.w[0] - 1));
+    int x = blockIdx.x * PB_T, y = blockIdx.y * PB_T, n = PB_T;
+    for (int s = P.steps; s >= 0; s--) {       // s = level index in P (steps = last level)
+      if (x < 0 || y < 0 || x + n > P.w[s] || y + n > P.h[s]) inside = false;
+      x = 2 * x - 2; y = 2 * y - 2; n = 2 * n + 3;
     }
   }
-  __syncthreads();
-  float *cur = bufA, *nxt = bufB;
-  for (int s = 1; s <= steps; s++) {
-    const int ki = steps - s + 1, ko = steps - s;        // region indices of source and destination
-    pb_scaledown(cur, n[ki], ox[ki], oy[ki], P.w[s - 1], P.h[s - 1], bufT, nxt, n[ko], ox[ko], oy[ko], P.sd);
-    // owned part of level s: the pixels under this tile, 8 * 2^(steps - s) on a side
-    const int on = PB_T << (steps - s);
-    pb_store(nxt, n[ko], ox[ko], oy[ko], P.img[s] + (size_t)img * P.stride[s], P.w[s], P.h[s], P.pitch[s],
-             blockIdx.x * on, blockIdx.y * on, on);
-    __syncthreads();
-    float *sw = cur; cur = nxt; nxt = sw;
-  }
+  if (P.steps == 3) { if (inside) pb_chain<3, false>(P, img, bufA, bufT, bufB); else pb_chain<3, true>(P, img, bufA, bufT, bufB); }
+  else if (P.steps == 2) { if (inside) pb_chain<2, false>(P, img, bufA, bufT, bufB); else pb_chain<2, true>(P, img, bufA, bufT, bufB); }
+  else { if (inside) pb_chain<1, false>(P, img, bufA, bufT, bufB); else pb_chain<1, true>(P, img, bufA, bufT, bufB); }
 }
 
 static int g_pb_configured[64];
