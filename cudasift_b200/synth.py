@@ -7,7 +7,10 @@ Descriptor sets: uniform[0,1) 128-vectors, L2-normalised (the pattern of match.c
 """
 import numpy as np
 
-from . import SIFT_DTYPE
+try:
+    from .records import SIFT_DTYPE
+except ImportError:      # loaded as a plain module (bench.py --impl reference never imports the package)
+    from records import SIFT_DTYPE
 
 
 def _blur(img, sigma):
