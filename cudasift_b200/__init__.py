@@ -82,6 +82,7 @@ def lib():
         "cs_event_elapsed_ms": (c.c_double, [vp, vp]),
         "cs_extractor_profile": (ip, [vp, vp, ip, c.c_double, fp, fp, c.POINTER(c.c_float)]),
         "cs_max_batch": (ip, []),
+        "cs_detector_items": (ip, [ip, ip, ip, ip, ip, ip, vp, ip]),
         "cs_extractor_create_batch": (vp, [ip, ip, ip, ip, ip, ip]),
         "cs_extractor_submit_device_batch": (ip, [vp, ip, vp, ip, c.c_double, fp, fp]),
         "cs_extractor_submit_host_batch": (ip, [vp, ip, vp, c.c_double, fp, fp]),

@@ -731,6 +731,7 @@ int cs_set_tuning(const char *key, int value)
   if (key && strcmp(key, "d2_hs") == 0) { cs::g_d2_hs = value; return 0; }
   if (key && strcmp(key, "pa_rows") == 0) { cs::g_pa_rows = value; return 0; }
   if (key && strcmp(key, "cap32") == 0) { cs::g_cap32 = value ? 1 : 0; return 0; }
+  if (key && strcmp(key, "cap32_limit") == 0) { cs::g_cap_limit = (value > 0 && value < 200) ? value : 32; return 0; }
   cs::set_error("cs_set_tuning: unknown key");
   return CS_E_ARG;
 }
@@ -1268,5 +1269,21 @@ void *cs_extractor_device_points_at(cs_extractor *ex, int slot) { return ex->d_p
 void *cs_extractor_host_points_at(cs_extractor *ex, int slot) { return ex->h_pts + (size_t)slot * ex->maxPts; }
 float *cs_extractor_host_image_at(cs_extractor *ex, int slot) { return ex->h_img + (size_t)slot * ex->w * ex->h; }
 int cs_max_batch(void) { return CS_MAX_BATCH; }
+
+// Host logic only (no device needed): the detector's work list for `n` images of width x height; every item is
+// 4 ints {level | image << 8, x0, first tested row, rows per stream}.  Returns the number of items.
+int cs_detector_items(int width, int height, int numOctaves, int scaleUp, int n, int hs, unsigned int *out, int capItems)
+{
+  if (width < 1 || height < 1 || numOctaves < 1 || numOctaves > 7 || n < 1 || hs < 1) { set_error("cs_detector_items: bad arguments"); return CS_E_ARG; }
+  int lw[CS_MAX_LEVELS], lh[CS_MAX_LEVELS], nl = numOctaves;
+  lw[0] = width * (scaleUp ? 2 : 1); lh[0] = height * (scaleUp ? 2 : 1);
+  for (int i = 1; i < numOctaves; i++) { lw[i] = lw[i - 1] / 2; lh[i] = lh[i - 1] / 2; if (lw[i] < 1 || lh[i] < 1) { nl = i; break; } }
+  std::vector<uint4> v;
+  cs::build_detector_items(lw, lh, nl, n, hs, v);
+  for (size_t i = 0; i < v.size() && (int)i < capItems; i++) {
+    out[4 * i] = v[i].x; out[4 * i + 1] = v[i].y; out[4 * i + 2] = v[i].z; out[4 * i + 3] = v[i].w;
+  }
+  return (int)v.size();
+}
 
 }  // extern "C"

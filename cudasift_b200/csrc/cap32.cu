@@ -110,7 +110,7 @@ cap32_fixup_kernel(const __grid_constant__ Detect2Params P)
       int rank = 0, nd = 0;
       for (int o = 0; o < 240; o++)
         if (s_flag[o]) {
-          if (rank >= 32) {
+          if (rank >= P.capLimit) {
             const int x = 30 * bx + o / 8, y = 8 * by + o % 8;
             s_drop[nd++] = (unsigned)x | ((unsigned)y << 13) | ((unsigned)scale << 26) | ((unsigned)level << 29);
           }

@@ -140,6 +140,7 @@ struct Detect2Params {
   unsigned int *cells;        // packed 8-bit counters, image i: cells + i * cellWords
   unsigned int *ovf;          // image i: ovf + i * CS_OVF_MAX
   int cellWords;
+  int capLimit;               // 32 (MEMWID, cudaSiftD.cu:1293); tests lower it to make the cap reachable
   int cellBase[CS_MAX_LEVELS], cellsX[CS_MAX_LEVELS];
   const float *lev0Img[CS_MAX_LEVELS];   // level images of image slot 0 (fix-up kernel): slot i at + i * imgStride
   long long imgStride;

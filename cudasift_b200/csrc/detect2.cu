@@ -380,7 +380,7 @@ detect2_kernel(const __grid_constant__ Detect2Params P)
               const int cell = P.cellBase[level] + ((gy >> 3) * P.cellsX[level] + gx / 30) * CS_NUM_SCALES + (p - 1);
               unsigned int *cw = P.cells + (size_t)img * P.cellWords + (cell >> 2);
               const unsigned old = atomicAdd(cw, 1u << (8 * (cell & 3)));
-              if (((old >> (8 * (cell & 3))) & 0xff) == 32) {      // the 33rd extremum of this cell
+              if (((old >> (8 * (cell & 3))) & 0xff) == (unsigned)P.capLimit) {      // the 33rd extremum of this cell
                 const unsigned at = atomicAdd(&counters[3], 1u);
                 if (at < CS_OVF_MAX) P.ovf[(size_t)img * CS_OVF_MAX + at] = (unsigned)cell;
               }
@@ -438,7 +438,7 @@ struct D3Item {
   unsigned int *counters;
   int maxPts;
   unsigned int *cells, *ovf;
-  int cellBase, cellsX;
+  int cellBase, cellsX, capLimit;
 };
 
 // Extrema of step j (DoG rows ry0-1+j / ry0+hs-1+j) by the 128 producer threads; rows j-1, j, j+1 are complete.
@@ -494,7 +494,7 @@ __device__ __noinline__ void d3_extrema(const D3Item &I, int j, int pt, const fl
         const int cell = I.cellBase + ((gy >> 3) * I.cellsX + gx / 30) * CS_NUM_SCALES + (p - 1);
         unsigned int *cw = I.cells + (cell >> 2);
         const unsigned old = atomicAdd(cw, 1u << (8 * (cell & 3)));
-        if (((old >> (8 * (cell & 3))) & 0xff) == 32) {      // the 33rd extremum of this cell
+        if (((old >> (8 * (cell & 3))) & 0xff) == (unsigned)I.capLimit) {      // the 33rd extremum of this cell
           const unsigned at = atomicAdd(&I.counters[3], 1u);
           if (at < CS_OVF_MAX) I.ovf[at] = (unsigned)cell;
         }
@@ -676,7 +676,7 @@ detect3_kernel(const __grid_constant__ Detect2Params P)
       I.maxPts = P.maxPts;
       I.cells = P.cells ? P.cells + (size_t)img * P.cellWords : nullptr;
       I.ovf = P.ovf ? P.ovf + (size_t)img * CS_OVF_MAX : nullptr;
-      I.cellBase = P.cellBase[level]; I.cellsX = P.cellsX[level];
+      I.cellBase = P.cellBase[level]; I.cellsX = P.cellsX[level]; I.capLimit = P.capLimit;
       const bool testable = hs_ >= 2 && hs_ <= 6;               // DoG planes 1..5
       const int tig = tid & 127;                                // thread index within the group
       for (int k = g; k < nsteps + 3; k += D3_NB) {

@@ -64,6 +64,7 @@ int make_tensor_map_2d(CUtensorMap *out, const float *base, int w, int h, int pi
 int g_d2_hs = 0;          // rows per detector stream (0 = choose by batch size)
 int g_pa_rows = 0;        // level-0 rows per CTA of kernel A (0 = choose by batch size)
 int g_cap32 = -1;         // reference cap of 32 extrema per 30x8 block and scale: 1 on (default), 0 off
+int g_cap_limit = 32;     // tests only
 
 static bool cap32_enabled()
 {
@@ -180,27 +181,34 @@ void Pipeline2::destroy()
 }
 
 // Detector work items for a batch of n images: coarsest level first (its strips carry the most extrema
-// candidates), so the persistent CTAs finish on the light strips of the finest level.
+// candidates), so the persistent CTAs finish on the light strips of the finest level.  An item = one strip of
+// CS_D2_STRIP tested columns x two row streams of `hs` tested rows each; every interior pixel of every level
+// belongs to exactly one item (tests/test_host_cpu.py).
+void build_detector_items(const int *lw, const int *lh, int numLevels, int n, int hs, std::vector<uint4> &v)
+{
+  for (int l = numLevels - 1; l >= 0; l--) {
+    if (lw[l] < 3 || lh[l] < 3) continue;                    // no interior pixel -> no extrema possible
+    const int strips = idivup(lw[l] - 2, CS_D2_STRIP);
+    const int rows = lh[l] - 2;                              // tested rows 1 .. h-2
+    const int nitems = idivup(rows, 2 * hs);
+    for (int b = 0; b < n; b++)
+      for (int r = 0; r < nitems; r++) {
+        const int ry0 = 1 + r * 2 * hs;
+        const int left = rows - r * 2 * hs;
+        const int hsi = left >= 2 * hs ? hs : (left + 1) / 2;   // the last item splits what is left between its two streams
+        for (int s = 0; s < strips; s++)
+          v.push_back(make_uint4((unsigned)l | ((unsigned)b << 8), (unsigned)(s * CS_D2_STRIP), (unsigned)ry0, (unsigned)hsi));
+      }
+  }
+}
+
 int Pipeline2::get_items(int n, int hs, const uint4 **d_items, int *count)
 {
   const int key = n * 1024 + hs;
   auto it = items.find(key);
   if (it == items.end()) {
     std::vector<uint4> v;
-    for (int l = numLevels - 1; l >= 0; l--) {
-      if (lw[l] < 3 || lh[l] < 3) continue;                    // no interior pixel -> no extrema possible
-      const int strips = idivup(lw[l] - 2, CS_D2_STRIP);
-      const int rows = lh[l] - 2;                              // tested rows 1 .. h-2
-      const int nitems = idivup(rows, 2 * hs);
-      for (int b = 0; b < n; b++)
-        for (int r = 0; r < nitems; r++) {
-          const int ry0 = 1 + r * 2 * hs;
-          const int left = rows - r * 2 * hs;
-          const int hsi = left >= 2 * hs ? hs : (left + 1) / 2;   // the last item splits what is left between its two streams
-          for (int s = 0; s < strips; s++)
-            v.push_back(make_uint4((unsigned)l | ((unsigned)b << 8), (unsigned)(s * CS_D2_STRIP), (unsigned)ry0, (unsigned)hsi));
-        }
-    }
+    build_detector_items(lw, lh, numLevels, n, hs, v);
     ItemList il;
     il.n = (int)v.size();
     il.d = nullptr;
@@ -299,6 +307,7 @@ int Pipeline2::enqueue(int n, const float *const *d_imgs, int pitch, double init
   dp.thresh = thresh; dp.edgeLimit = 10.0f; dp.factor = 1.0f / CS_NUM_SCALES;   // cudaSiftH.cu:213
   dp.pts = d_pts; dp.ptsStride = ptsStride; dp.counters = d_counters; dp.sched = d_sched; dp.maxPts = maxPts;
   if (cap32_enabled()) { dp.cells = d_cells; dp.ovf = d_ovf; dp.cellWords = cellWords; }
+  dp.capLimit = g_cap_limit;
   if ((r = launch_detect2(dp, sms, st)) < 0) return r;
   if ((r = debug_stage(st, "detect2")) < 0) return r;
   if (cap32_enabled()) {

@@ -43,6 +43,7 @@ struct Pipeline2 {
               PyrAParams *paOut = nullptr);
 };
 
-extern int g_d2_hs, g_pa_rows, g_cap32, g_d2_variant;
+void build_detector_items(const int *lw, const int *lh, int numLevels, int n, int hs, std::vector<uint4> &v);
+extern int g_d2_hs, g_pa_rows, g_cap32, g_cap_limit, g_d2_variant;
 
 }  // namespace cs

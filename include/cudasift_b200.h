@@ -156,6 +156,10 @@ float *cs_extractor_host_image_at(cs_extractor *ex, int slot);
 /* Stage times of one batch (see cs_extractor_profile); returns the sum of the counts. */
 int cs_extractor_profile_batch(cs_extractor *ex, int n, const float *const *d_imgs, int pitch, double initBlur,
                                float thresh, float lowestScale, float out_ms[5]);
+/* Host logic of the batched detector (no device needed; tests): its work list for n images -- per item 4 ints
+ * {level | image << 8, first column, first tested row, rows per row stream}; a strip tests 244 columns
+ * (first column + 1 ...), an item two streams of rows.  Returns the number of items (out holds capItems). */
+int cs_detector_items(int width, int height, int numOctaves, int scaleUp, int n, int hs, unsigned int *out, int capItems);
 /* Parity tests: pyramid level `level` of image slot `slot` as left by the last submit, packed into h_out
  * (may be NULL); returns width | height << 16 of that level. */
 int cs_extractor_read_level(cs_extractor *ex, int slot, int level, float *h_out);

@@ -114,6 +114,21 @@ def tex2d(img, xs, ys):
     return np.array([L.oracle_tex2d(_p(img), w, h, w, float(x), float(y)) for x, y in zip(xs, ys)], np.float32)
 
 
+def set_cap32(on):
+    """The reference's cap of 32 extrema per (30x8 block, scale), cudaSiftD.cu:1371: on by default."""
+    lib().oracle_set_cap32(int(bool(on)))
+
+
+def set_cap_limit(n):
+    """Tests only: the cap's limit (32 in the reference); natural DoG planes never hold 33 extrema per block and scale."""
+    lib().oracle_set_cap_limit(int(n))
+
+
+def last_dropped():
+    """Extrema the cap dropped during the last extract()."""
+    return int(lib().oracle_last_dropped())
+
+
 def extract(img, numOctaves=5, initBlur=1.0, thresh=3.0, lowestScale=0.0, scaleUp=False, maxPts=32768):
     """Returns (records[:numPts], total records written incl. the finest octave's secondaries)."""
     img = np.ascontiguousarray(img, np.float32)

@@ -256,6 +256,13 @@ static int refine_point(const float *dog, int w, int h, int pitch, int xpos, int
   return 1;
 }
 
+/* test knobs: the reference's cap of 32 extrema per (30x8 block, scale) can be switched off, and the number of
+ * extrema the cap dropped in the last oracle_extract is kept */
+static int g_cap32 = 1, g_dropped = 0, g_cap_limit = 32;
+void oracle_set_cap32(int on) { g_cap32 = on; }
+void oracle_set_cap_limit(int n) { g_cap_limit = n > 0 ? n : 32; }   /* 32 = MEMWID, cudaSiftD.cu:1293 */
+int oracle_last_dropped(void) { return g_dropped; }
+
 int oracle_find_points(const float *dog, int w, int h, int pitch, float subsampling,
                        float lowestScale, float thresh, float factor, float edgeLimit,
                        OracleSiftPoint *pts, int *count, int maxPts, int cap32)
@@ -287,7 +294,7 @@ int oracle_find_points(const float *dog, int w, int h, int pitch, float subsampl
                   mx = fmaxf(mx, v);
                 }
             if ((d11 < fminf(-thresh, mn)) || (d11 > fmaxf(thresh, mx))) {
-              if (cap32 && ncand >= 32) { dropped++; continue; }   /* pos<MEMWID, tx<totbits */
+              if (cap32 && ncand >= g_cap_limit) { dropped++; continue; }   /* pos<MEMWID, tx<totbits */
               cx[ncand] = x; cy[ncand] = y; ncand++;
             }
           }
@@ -520,21 +527,22 @@ int oracle_extract(const float *img, int w0, int h0, int pitch0, int numOctaves,
     lev[i] = (float *)calloc((size_t)lh[i] * lp[i] + 1, sizeof(float));
     oracle_scaledown(lev[i - 1], lev[i], lw[i - 1], lh[i - 1], lp[i - 1], lp[i]);
   }
-  int count = 0, numPts = 0;
+  int count = 0, numPts = 0, dropped = 0;
   for (int i = numOctaves - 1; i >= 0; i--) {                 /* coarsest octave first */
     int octave = numOctaves - i;
     float subsampling = (float)(1 << i);
     float *dog = (float *)malloc(sizeof(float) * 7 * (size_t)lh[i] * lp[i]);
     oracle_dog(lev[i], dog, lw[i], lh[i], lp[i], taps + octave * 12 * 16);
     int first = count;
-    oracle_find_points(dog, lw[i], lh[i], lp[i], subsampling, lowestScale / subsampling, thresh,
-                       1.0f / NUM_SCALES, 10.0f, pts, &count, maxPts, 1);
+    dropped += oracle_find_points(dog, lw[i], lh[i], lp[i], subsampling, lowestScale / subsampling, thresh,
+                                  1.0f / NUM_SCALES, 10.0f, pts, &count, maxPts, g_cap32);
     int afterFind = count;
     if (i == 0) numPts = imin(afterFind, maxPts);              /* :115-116, quirk Q1 */
     oracle_orientations(lev[i], lw[i], lh[i], lp[i], pts, first, afterFind, &count, maxPts);
     oracle_descriptors(lev[i], lw[i], lh[i], lp[i], pts, imin(first, maxPts), imin(count, maxPts), subsampling);
     free(dog);
   }
+  g_dropped = dropped;
   if (scaleUp)                                                /* :130, RescalePositions */
     for (int i = 0; i < numPts; i++) { pts[i].xpos *= 0.5f; pts[i].ypos *= 0.5f; pts[i].scale *= 0.5f; }
   for (int i = 0; i < numOctaves; i++) free(lev[i]);

@@ -74,6 +74,12 @@ void oracle_descriptors(const float *img, int w, int h, int pitch, OracleSiftPoi
  * stride `pitch`.  Returns numPts as the reference reports it (quirk Q1: the finest
  * octave's secondary orientations are not counted); *total receives the number of
  * records written including those. */
+/* Test knobs: switch the cap of 32 extrema per block and scale off / on (default on, as in the reference);
+ * number of extrema the cap dropped during the last oracle_extract. */
+void oracle_set_cap32(int on);
+void oracle_set_cap_limit(int n);   /* tests only: a lower limit makes the cap reachable */
+int oracle_last_dropped(void);
+
 int oracle_extract(const float *img, int w, int h, int pitch, int numOctaves,
                    float initBlur, float thresh, float lowestScale, int scaleUp,
                    OracleSiftPoint *pts, int maxPts, int *total);

@@ -65,25 +65,45 @@ def test_extract_deterministic(cs):
 
 def test_extract_vs_reference(cs, reflib):
     """The headline parity test: reference ExtractSift and the product on identical inputs.
-    Tolerance from BASELINE.json: x/y/scale/orientation and descriptors within 1e-3."""
+    BASELINE.json asks for x/y/scale/orientation and descriptors within 1e-3 relative; what is asserted is what was
+    measured: positions, scales, sharpness and edgeness BIT-IDENTICAL, orientation and descriptors within twice the
+    reference's own run-to-run noise (its histograms are accumulated with shared-memory float atomics, quirk Q3)."""
     if reflib is None:
         pytest.skip("oracle/_ref/libcudasift_ref.so not present")
-    cases = [(synth_image(1280, 960, seed=1000), 3.0), (synth_image(1920, 1080, seed=1000), 3.0)]
+    cases = [(synth_image(1280, 960, seed=1000), dict(thresh=3.0)), (synth_image(1920, 1080, seed=1000), dict(thresh=3.0)),
+             (synth_image(640, 480, seed=7), dict(thresh=2.0, scaleUp=True)),
+             (synth_image(800, 600, seed=8), dict(thresh=3.0, numOctaves=1)),
+             (synth_image(800, 600, seed=8), dict(thresh=3.0, numOctaves=3))]
     left = _left()
-    if left is not None:
-        cases.append((left, 4.5))                       # config #1: data/left.pgm, mainSift.cpp:59
-    for arr, thresh in cases:
-        r1 = canon(reflib.extract(arr, thresh=thresh))
-        r2 = canon(reflib.extract(arr, thresh=thresh))
-        mine = canon(_extract(cs, arr, thresh=thresh))
-        noise = compare_sets(r1, r2)                    # the reference against itself (Q3/Q4)
-        rep = compare_sets(mine, r1)
-        print("ref-vs-ref", noise)
-        print("mine-vs-ref", rep)
-        assert len(mine) == len(r1), (len(mine), len(r1))
-        assert rep["pairs"] >= noise["pairs"] - max(2, 0.002 * len(r1)), (rep, noise)
-        assert rep["pos_err"] < 1e-3 * 2 and rep["scale_rel"] < 1e-3 and rep["ori_err"] < 0.36, rep
-        assert rep["desc_bad"] <= max(noise["desc_bad"] + 2, 0.002 * rep["pairs"]), (rep, noise)
+    if left is None:                                    # config #1 must not vanish silently
+        pytest.fail("oracle/_ref is present but data/left.pgm (BASELINE config #1) or cv2 is missing")
+    cases.append((left, dict(thresh=4.5)))              # config #1: data/left.pgm, mainSift.cpp:59
+    for arr, kw in cases:
+        r1 = canon(reflib.extract(arr, **kw))
+        r2 = canon(reflib.extract(arr, **kw))
+        mine = canon(_extract(cs, arr, **kw))
+        assert len(r1) == len(r2) == len(mine) > 100, (kw, len(r1), len(r2), len(mine))
+        for f in ("xpos", "ypos", "scale", "sharpness", "edgeness", "subsampling"):
+            assert np.array_equal(mine[f], r1[f]), (kw, f)
+        do = lambda a, b: np.minimum(np.abs(a - b) % 360.0, 360.0 - np.abs(a - b) % 360.0)
+        ori_noise = float(do(r1["orientation"], r2["orientation"]).max())
+        ori_err = float(do(mine["orientation"], r1["orientation"]).max())
+        fin = np.isfinite(r1["data"]).all(axis=1) & np.isfinite(r2["data"]).all(axis=1) & np.isfinite(mine["data"]).all(axis=1)
+        dn = np.abs(r1["data"][fin] - r2["data"][fin]).max(axis=1)
+        de = np.abs(mine["data"][fin] - r1["data"][fin]).max(axis=1)
+        d_noise, d_err = float(dn.max()), float(de.max())
+        bad_noise, bad_err = int((dn > 2e-5).sum()), int((de > 2e-5).sum())
+        print(kw, "points", len(mine), "ori noise/err", ori_noise, ori_err, "desc max noise/err", d_noise, d_err,
+              "rows > 2e-5 noise/err", bad_noise, bad_err, "median err", float(np.median(de)))
+        assert ori_err <= max(2.0 * ori_noise, 1e-3), (kw, ori_err, ori_noise)
+        # a last-bit difference of the orientation moves sample positions across the texture unit's 1/256 coordinate
+        # grid: a few descriptors differ by ~1e-4 (the reference does the same between two of its own runs)
+        assert float(np.median(de)) <= 1e-6, (kw, float(np.median(de)))
+        # measured on the B200 (6 cases): rows > 2e-5: reference vs itself 1..14, product vs reference 0..10; max 2.0e-4 both
+        assert bad_err <= 2 * bad_noise + 5, (kw, bad_err, bad_noise)
+        assert d_err <= max(2.0 * d_noise, 3e-4), (kw, d_err, d_noise)
+        assert d_err <= 1e-3 and ori_err <= 0.36                    # BASELINE.json: 1e-3 (orientation: of 360 degrees)
+        assert np.array_equal(np.isfinite(mine["data"]).all(axis=1), np.isfinite(r1["data"]).all(axis=1))   # quirk Q21 rows
 
 
 def test_cxx_api_equals_c_abi(cs, selflib):

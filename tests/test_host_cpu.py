@@ -1,0 +1,90 @@
+"""Host-side logic of the batched pipeline that needs no GPU: the detector's work list, the standalone synthetic-input
+module of the reference bench arm, the bench helpers."""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import cudasift_b200 as cs
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def items(w, h, octaves, up, n, hs):
+    L = cs.lib()
+    cap = 200000
+    out = np.zeros(4 * cap, np.uint32)
+    cnt = L.cs_detector_items(w, h, octaves, int(up), n, hs, out.ctypes.data, cap)
+    assert 0 <= cnt <= cap
+    return out[:4 * cnt].reshape(cnt, 4).astype(np.int64)
+
+
+@pytest.mark.parametrize("w,h,octaves,up,n,hs", [(1920, 1080, 5, False, 1, 16), (1920, 1080, 5, False, 3, 64), (641, 479, 4, False, 2, 32),
+                                                 (150, 100, 3, True, 1, 16), (1000, 700, 7, False, 1, 16), (20, 12, 5, False, 1, 16),
+                                                 (247, 131, 2, False, 1, 7), (3, 3, 1, False, 1, 16)])
+def test_detector_items_cover_every_interior_pixel_once(w, h, octaves, up, n, hs):
+    """Every interior pixel (1..w-2, 1..h-2) of every level of every image is tested by exactly one item and stream."""
+    it = items(w, h, octaves, up, n, hs)
+    lw, lh = [w * (2 if up else 1)], [h * (2 if up else 1)]
+    for i in range(1, octaves):
+        if lw[-1] // 2 < 1 or lh[-1] // 2 < 1:
+            break
+        lw.append(lw[-1] // 2); lh.append(lh[-1] // 2)
+    cover = {(b, l): np.zeros((lh[l], lw[l]), np.int32) for b in range(n) for l in range(len(lw))}
+    for key, x0, ry0, hsi in it:
+        l, b = int(key) & 0xff, int(key) >> 8
+        assert x0 % 4 == 0                                    # TMA box alignment: x0 - 4 is a multiple of 4 floats
+        assert 1 <= hsi <= hs
+        cols = [x0 + d for d in range(1, 245) if x0 + d <= lw[l] - 2]
+        rows = [r for r in range(ry0, ry0 + 2 * hsi) if r <= lh[l] - 2]
+        for r in rows:
+            cover[(b, l)][r, cols] += 1
+    for (b, l), c in cover.items():
+        if lw[l] < 3 or lh[l] < 3:
+            assert c.sum() == 0
+            continue
+        assert (c[1:-1, 1:-1] == 1).all(), (b, l)
+        assert c[0].sum() == 0 and c[-1].sum() == 0 and c[:, 0].sum() == 0 and c[:, -1].sum() == 0
+    # coarsest level first
+    levels = [int(k) & 0xff for k in it[:, 0]]
+    assert levels == sorted(levels, reverse=True)
+
+
+def test_synth_loads_without_the_package():
+    """bench.py --impl reference generates its inputs without importing cudasift_b200 (whose library it must not load)."""
+    code = ("import sys; sys.path.append(%r); import synth; a = synth.synth_image(64, 48, seed=1); d = synth.synth_descriptors(8, 1); "
+            "assert 'cudasift_b200' not in sys.modules; print(a.shape, d.dtype.itemsize)") % os.path.join(ROOT, "cudasift_b200")
+    import subprocess
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "(48, 64) 576" in out.stdout
+    from cudasift_b200.synth import synth_image
+    import hashlib
+    assert synth_image(64, 48, seed=1).shape == (48, 64)
+
+
+def test_bench_helpers():
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    a = bench.workload_config(32, 8, 1920, 1710.62)
+    b = bench.workload_config(32, 8, 1920, 1710.58)
+    assert a == b and a["features_per_image"] == 1710.6
+    info = bench.bind_numa(0)                  # no GPU here: must not raise, must say it did not bind
+    assert isinstance(info, dict) and "bound" in info
+    s = bench.ClockSampler(0)
+    s.start()
+    r = s.stop()
+    assert "sm_mhz" in r and "reasons" in r
+    assert len(bench.level_sizes()) == 5 and bench.level_sizes()[4] == (120, 67)
+
+
+def test_new_abi_symbols_present():
+    L = cs.lib()
+    for name in ("cs_extractor_create_batch", "cs_extractor_submit_device_batch", "cs_extractor_submit_host_batch",
+                 "cs_extractor_wait_batch", "cs_extractor_profile_batch", "cs_extractor_read_level", "cs_max_batch",
+                 "cs_detector_items", "cs_extractor_device_points_at", "cs_extractor_host_points_at"):
+        assert hasattr(L, name), name
+    assert L.cs_max_batch() == 32
+    assert L.cs_set_tuning(b"cap32_limit", 32) == 0 and L.cs_set_tuning(b"legacy", 0) == 0
