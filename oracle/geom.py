@@ -3,9 +3,11 @@
 Follows geomFuncs.cpp:6-72 of the reference line by line (float32 for den/dx/dy/err, float64 for the
 8x8 normal equations), with numpy.linalg.solve standing in for cv::solve(DECOMP_CHOLESKY).
 
-PARITY UNPINNED: the reference routine needs OpenCV, which is not in this image, so the
-reference itself cannot be run here and it has no golden vectors; the restatement is checked only
-against geometry with a known answer (tests/test_homography.py).
+Pinned (round 2): the reference routine itself needs OpenCV's C++ headers, which this image lacks, but cv2
+(OpenCV 4.13) is importable, so improve_homography_cv2() below restates geomFuncs.cpp statement by statement
+around the very cv::solve(DECOMP_CHOLESKY) the reference calls; tests/golden/improve_homography.npz holds its
+outputs (tests/golden/make_geom_golden.py) and tests/test_homography.py checks this vectorised restatement and
+the product's ImproveHomography against them.
 """
 import numpy as np
 
@@ -45,3 +47,54 @@ def improve_homography(pts, homography, numLoops=5, minScore=0.0, maxAmbiguity=0
     numfit = int((e < limit).sum())                             # :66-67
     out = np.concatenate([A, [1.0]]).astype(f32)
     return out, numfit, np.sqrt(e).astype(f32)
+
+
+def improve_homography_cv2(pts, homography, numLoops=5, minScore=0.0, maxAmbiguity=0.80, thresh=3.0):
+    """The reference routine statement by statement (geomFuncs.cpp:6-72), with the reference's own third-party
+    solver: cv2.solve(M, X, flags=cv2.DECOMP_CHOLESKY) is the Python binding of the cv::solve call at :55
+    (OpenCV 4.13 in this image; the reference pins no version).  Point-by-point accumulation in the reference's
+    order and types (float products for Y[6], Y[7]; double for M, X; float for den/dx/dy/err).  This is what
+    pins improve_homography() above and the product's ImproveHomography: tests/golden/improve_homography.npz is
+    generated from it (tests/golden/make_geom_golden.py) and tests/test_homography.py re-runs it when cv2 imports."""
+    import cv2
+    f32, f64 = np.float32, np.float64
+    h = np.asarray(homography, f32).reshape(9)
+    A = np.array([f64(h[i] / h[8]) for i in range(8)], f64).reshape(8, 1)      # :20-21 (float division)
+    limit = f32(thresh) * f32(thresh)
+    minScore, maxAmbiguity = f32(minScore), f32(maxAmbiguity)
+    xs, ys = pts["xpos"].astype(f32), pts["ypos"].astype(f32)
+    us, vs = pts["match_xpos"].astype(f32), pts["match_ypos"].astype(f32)
+    sc, am = pts["score"].astype(f32), pts["ambiguity"].astype(f32)
+
+    def residual(A, x, y, u, v, one):
+        a = A[:, 0]
+        den = f32(a[6] * f64(x) + a[7] * f64(y) + one)                         # :29 / :61
+        dx = f32((a[0] * f64(x) + a[1] * f64(y) + a[2]) / f64(den) - f64(u))
+        dy = f32((a[3] * f64(x) + a[4] * f64(y) + a[5]) / f64(den) - f64(v))
+        return f32(f32(dx * dx) + f32(dy * dy))
+
+    for _ in range(numLoops):
+        M = np.zeros((8, 8), f64)
+        X = np.zeros((8, 1), f64)
+        for i in range(len(pts)):
+            x, y, u, v = xs[i], ys[i], us[i], vs[i]
+            if sc[i] < minScore or am[i] > maxAmbiguity:                       # :26
+                continue
+            err = residual(A, x, y, u, v, f64(f32(1.0)))
+            wei = f64(1.0) if err < limit else f64(0.0)                        # :33
+            Y = np.array([x, y, 1.0, 0.0, 0.0, 0.0, -f32(x * u), -f32(y * u)], f64)   # :34-39
+            M += np.outer(Y, Y) * wei                                          # :40-42
+            X += (Y * f64(u) * wei).reshape(8, 1)                              # :43
+            Y = np.array([0.0, 0.0, 0.0, x, y, 1.0, -f32(x * v), -f32(y * v)], f64)   # :44-49
+            M += np.outer(Y, Y) * wei
+            X += (Y * f64(v) * wei).reshape(8, 1)
+        ok, sol = cv2.solve(M, X, flags=cv2.DECOMP_CHOLESKY)                   # :55
+        A = sol if ok else np.zeros((8, 1), f64)
+    numfit = 0
+    errs = np.zeros(len(pts), f32)
+    for i in range(len(pts)):
+        err = residual(A, xs[i], ys[i], us[i], vs[i], f64(1.0))
+        numfit += int(err < limit)                                             # :65-66
+        errs[i] = np.sqrt(err)                                                 # :67
+    out = np.concatenate([A[:, 0], [1.0]]).astype(f32)                         # :69-71
+    return out, numfit, errs

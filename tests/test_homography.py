@@ -104,3 +104,38 @@ def test_improve_homography_host():
     assert np.array_equal(Hz.reshape(9)[:8], np.zeros(8, np.float32)) and Hz[2, 2] == 1.0
     Hzo, nzo, _ = improve_homography(p, H0, 2, 2.0, 0.0, 3.0)
     assert nz == nzo and np.array_equal(Hz.reshape(9), Hzo)
+
+
+def _golden():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "improve_homography.npz"))
+
+
+def test_improve_homography_pinned_by_opencv():
+    """the vectorised restatement AND the product against golden vectors produced by the reference's
+    own solver (cv::solve(DECOMP_CHOLESKY) through cv2 inside a statement-by-statement port of geomFuncs.cpp:6-72);
+    the port is re-run live when cv2 imports."""
+    import cudasift_b200 as cs
+    from oracle.geom import improve_homography, improve_homography_cv2
+    g = _golden()
+    p, H0 = g["points"], g["H0"]
+    p2, _ = planted(n=900, seed=11, noise=0.25)
+    assert p.tobytes() == p2.tobytes()                       # the fixture's inputs are the seeded ones
+    try:
+        import cv2  # noqa: F401
+        live = True
+    except ImportError:
+        live = False
+    for k, (loops, mins, maxa, thr) in enumerate(g["cases"]):
+        Hg, ng, eg = g["H_%d" % k], int(g["numfit_%d" % k]), g["err_%d" % k]
+        Ho, no, eo = improve_homography(p, H0, int(loops), mins, maxa, thr)
+        q = p.copy()
+        Hp, npd = cs.ImproveHomography(q, H0, int(loops), mins, maxa, thr)
+        for H, n, e, who in ((Ho, no, eo, "oracle"), (Hp.reshape(9), npd, q["match_error"], "product")):
+            assert n == ng, (who, k, n, ng)
+            # float32 outputs of an 8x8 double solve: different summation orders agree to a few ulp
+            assert np.allclose(H, Hg, rtol=2e-6, atol=1e-9), (who, k, H, Hg)
+            assert np.allclose(e, eg, rtol=1e-4, atol=2e-4), (who, k)
+        if live:
+            Hc, nc, ec = improve_homography_cv2(p, H0, int(loops), mins, maxa, thr)
+            assert nc == ng and np.array_equal(Hc, Hg) and np.array_equal(ec, eg)
