@@ -68,9 +68,10 @@ int launch_u8_to_float(const uint8_t *src, int srcPitch, float *dst, int dstPitc
 
 // ---- fused, batched pyramid (pyramid2.cu) ---------------------------------------------------
 #define CS_MAX_BATCH 32       // images per launch (input tensor maps travel as kernel parameters)
-#define CS_PA_OWN 240         // level-0 columns a CTA of kernel A owns
+#define CS_PA_OWN 120         // level-0 columns a warp of kernel A owns
+#define CS_PA_BOX 136         // staged columns per input row (TMA box width): own + 8 left + 8 right
 struct PyrAParams {
-  CUtensorMap inMaps[CS_MAX_BATCH];   // input images, box 256 x 1
+  CUtensorMap inMaps[CS_MAX_BATCH];   // input images, box 136 x 1
   float *lev0; long long lev0Stride;  // image i writes lev0 + i * lev0Stride (floats)
   float *lev1; long long lev1Stride;  // NULL: no ScaleDown (single octave)
   int w, h, p0, w1, h1, p1;

@@ -137,7 +137,7 @@ int Pipeline2::init(int w, int h, int octaves, bool up, int maxBatch, float *are
       if ((r = make_tensor_map_2d(&maps[(size_t)b * CS_MAX_LEVELS + i], level(b, i), lw[i], lh[i], lp[i], 256, 1)) < 0) return r;
     }
     if (up) {
-      int r = make_tensor_map_2d(&upMaps[b], arena + (size_t)b * perImage + upOff, lw[0], lh[0], lp[0], 256, 1);
+      int r = make_tensor_map_2d(&upMaps[b], arena + (size_t)b * perImage + upOff, lw[0], lh[0], lp[0], CS_PA_BOX, 1);
       if (r < 0) return r;
     }
   }
@@ -229,7 +229,7 @@ int Pipeline2::fill_pyr_a(PyrAParams &pa, int n, const float *const *d_imgs, int
   for (int b = 0; b < n; b++) {
     if (scaleUp) pa.inMaps[b] = upMaps[b];
     else {
-      int r = make_tensor_map_2d(&pa.inMaps[b], d_imgs[b], w0, h0, pitch, 256, 1);
+      int r = make_tensor_map_2d(&pa.inMaps[b], d_imgs[b], w0, h0, pitch, CS_PA_BOX, 1);
       if (r < 0) return r;
     }
   }
@@ -242,7 +242,7 @@ int Pipeline2::fill_pyr_a(PyrAParams &pa, int n, const float *const *d_imgs, int
   float sigma = (float)(initBlur > (double)0.001f ? initBlur : (double)0.001f);   // cudaSiftH.cu:112
   lowpass_taps(sigma, pa.lp.k);
   pa.sd = sdTaps;
-  int rows = g_pa_rows > 0 ? g_pa_rows : (n >= 8 ? 64 : (n >= 2 ? 32 : 16));
+  int rows = g_pa_rows > 0 ? g_pa_rows : (n >= 8 ? 120 : (n >= 2 ? 64 : 32));   // rows per warp: halo of 12 rows each
   rows = (rows + 1) & ~1;
   pa.rowsPerCta = rows;
   pa.stripsX = idivup(lw[0], CS_PA_OWN);

@@ -4,12 +4,12 @@
 // per-pixel arithmetic as in pyramid.cu (pinned to the reference's sm_100 SASS), so every level is bit-identical
 // to the reference's.
 //
-// Kernel A: a CTA (64 threads) owns a strip of 240 columns x R rows of the full-resolution level and marches down
-// the rows.  Input rows arrive by TMA (cp.async.bulk.tensor.2d, 256 x 1 boxes, 8 rows in flight per CTA, row index
-// clamped by the issuing thread); each thread filters 4 columns: horizontal 9-tap from the staged row, vertical
-// 9-tap over its own column history (a 16-row ring in shared memory that only the owning thread touches, so no
-// barrier), one 128-bit store of the level-0 row.  The same row is handed to the 5-tap ScaleDown through shared
-// memory, so level 1 is produced without re-reading level 0: HBM traffic per image = read input + write level 0
+// Kernel A: a WARP owns a strip of 120 columns x R rows of the full-resolution level and marches down the rows; warps
+// never talk to each other, so there is no CTA barrier anywhere.  Input rows arrive by TMA (cp.async.bulk.tensor.2d,
+// 136 x 1 boxes, 8 rows in flight per warp, row index clamped by the issuing lane); each lane filters 4 columns:
+// horizontal 9-tap from the staged row, vertical 9-tap over its own 9-row register window (packed FFMA2/FADD2 on column
+// pairs), one 128-bit store of the level-0 row.  The same row is handed to the 5-tap ScaleDown through three warp
+// shuffles, so level 1 is produced without re-reading level 0: HBM traffic per image = read input + write level 0
 // + write level 1 (the reference: + one more read of level 0).
 // Kernel B: a CTA owns an 8x8 tile of the coarsest level it produces and computes the up to three levels above it
 // for that tile in shared memory (85x85 -> 41x41 -> 19x19 -> 8x8), writing the part of every level it owns: the
@@ -47,122 +47,166 @@ __device__ __forceinline__ float sd_v(const Taps5 &t, float r0, float r1, float 
   return s;
 }
 
-#define PA_THREADS 64
-#define PA_IW 256          // staged input columns: x0-8 .. x0+247
-#define PA_NS 8            // input rows in flight per CTA
+#define PA_THREADS 32      // one warp per CTA: a strip is private to its warp, so the march needs no CTA barrier
+#define PA_IW CS_PA_BOX    // staged input columns x0-8 .. x0+127 (one TMA box row)
+#define PA_SLOT 160        // floats between ring slots (640 B: TMA destinations are 128-byte aligned)
+#define PA_NS 9            // input rows in flight per warp = depth of the register window, so ring slot = window slot
 
-// One marching step.  PH: window slot that receives the horizontally filtered row u (compile-time: the step loop
-// is unrolled by 9).  The 9-row window of horizontally filtered rows lives in registers (one float4 per row).
+// Per-warp constants of the march ...
 struct PaCtx {
-  int w, h, x0, R0, R1, ya, yb, ia, ib, Y1b, p0, p1, w1, cb, x1;
-  bool edge, act, own, sd;
-  float *lev0, *lev1;
+  int w, h, x0, R0, R1, ia, seqEnd, Y1b, p0, p1, w1, cb, x1;
+  bool own, sd;
+};
+// ... and what changes from step to step
+struct PaRun {
+  int seq;          // input row ia + seq
+  int y;            // level-0 row this step produces (ia + seq - 4)
+  int nextY1, trig; // next level-1 row and the level-0 row that completes it
+  unsigned par;     // mbarrier phase the next wait expects (flips after slot 8: slots 0..7 then start their next use)
+  float *out0;      // level-0 row y, column cb
+  float *out1;      // level-1 row nextY1, column x1
 };
 
-template <int PH>
-__device__ __forceinline__ void pa_step(const PaCtx &C, int u, int &nextY1, float4 (&W)[9], const Taps9 &lp, const Taps5 &sdk,
-                                        float (*s_in)[PA_IW], float (*s_l0)[PA_IW], float2 (*s_h2)[PA_THREADS],
-                                        uint64_t *s_full, const CUtensorMap *map)
+// One marching step = input row ia+seq (row index clamped by the TMA issuer, which reproduces the reference's clamped
+// row reads: cudaSiftD.cu:1997).  PH: window slot AND ring slot of this step (compile-time: the step loop is
+// unrolled by 9).  The 9-row window lives in registers as two packed pairs per row (columns cb,cb+1 | cb+2,cb+3), so
+// the vertical pass runs on FFMA2/FADD2.  EDGE: the strip touches the left or right image border (columns are
+// clamped by the reading lane; the ScaleDown neighbours go through shared memory instead of shuffles).
+// MAIN: the window is full -> vertical pass, level-0 store, ScaleDown.
+template <int PH, bool EDGE, bool MAIN>
+__device__ __forceinline__ void pa_step(const PaCtx &C, PaRun &R, f32x2 (&W)[9][2], const Taps9 &lp, const Taps5 &sdk,
+                                        float *s_in, float2 *s_h2, float *s_l0, uint64_t *s_full, const CUtensorMap *map)
 {
-  const int t = threadIdx.x;
-  if (u <= C.ib) {
-    // ---------------------------------------------------------------- horizontal 9-tap of input row u
-    const int seq = u - C.ia, slot = seq & (PA_NS - 1);
-    mbarrier_wait(&s_full[slot], (seq >> 3) & 1);
-    if (C.act) {
-      float v[12];
-      if (!C.edge) {
-        const float4 *p = reinterpret_cast<const float4 *>(&s_in[slot][4 * t]);
-        const float4 a = p[0], b = p[1], c = p[2];
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 12; i++) v[i] = s_in[slot][clampi2(C.cb - 4 + i, 0, C.w - 1) - (C.x0 - 8)];
-      }
-      float o[4];
-#pragma unroll
-      for (int d = 0; d < 4; d++)
-        o[d] = pa_sym9(lp, v[d + 4], __fadd_rn(v[d + 5], v[d + 3]), __fadd_rn(v[d + 6], v[d + 2]),
-                       __fadd_rn(v[d + 7], v[d + 1]), __fadd_rn(v[d + 8], v[d]));
-      W[PH] = make_float4(o[0], o[1], o[2], o[3]);
-      if (u == 0) {                         // rows above the image are row 0 (cudaSiftD.cu:1997 clamps the row index)
-#pragma unroll
-        for (int i = 0; i < 9; i++) W[i] = W[PH];
-      }
-    }
-  } else if (C.act) {
-    W[PH] = W[(PH + 8) % 9];                // rows below the image are row h-1
+  const int lane = threadIdx.x;
+  float *rowp = s_in + PH * PA_SLOT;
+  mbarrier_wait(&s_full[PH], R.par);
+  // ------------------------------------------------------------------ horizontal 9-tap of the input row
+  float v[12];
+  {
+    const float4 *p = reinterpret_cast<const float4 *>(rowp + 4 * lane);       // columns cb-4 .. cb+7
+    const float4 a = p[0], b = p[1], c = p[2];
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
   }
-  const int y = u - 4;
-  const bool row = y >= C.ya && y <= C.yb;
-  if (row && C.act) {
-    // ------------------------------------------------------------------ vertical 9-tap -> level-0 row y
-    // window order: oldest = slot PH+1 (row y-4) ... newest = slot PH (row y+4)
-#define PAW(i) W[(PH + 1 + (i)) % 9]
-    float4 o;
-#define PAV(f) pa_sym9(lp, PAW(4).f, __fadd_rn(PAW(3).f, PAW(5).f), __fadd_rn(PAW(2).f, PAW(6).f), __fadd_rn(PAW(1).f, PAW(7).f), __fadd_rn(PAW(0).f, PAW(8).f))
-    o.x = PAV(x); o.y = PAV(y); o.z = PAV(z); o.w = PAV(w);
+  if (EDGE) {
+    if (C.cb - 4 < 0 || C.cb + 7 > C.w - 1) {                // cudaSiftD.cu:2005-2008: clamped column reads
+#pragma unroll
+      for (int i = 0; i < 12; i++) v[i] = rowp[clampi2(C.cb - 4 + i, 0, C.w - 1) - (C.x0 - 8)];
+    }
+  }
+  float o[4];
+#pragma unroll
+  for (int d = 0; d < 4; d++)
+    o[d] = pa_sym9(lp, v[d + 4], __fadd_rn(v[d + 5], v[d + 3]), __fadd_rn(v[d + 6], v[d + 2]),
+                   __fadd_rn(v[d + 7], v[d + 1]), __fadd_rn(v[d + 8], v[d]));
+  W[PH][0] = pk2(o[0], o[1]);
+  W[PH][1] = pk2(o[2], o[3]);
+  __syncwarp();                                              // every lane has consumed the slot
+  if (lane == 0 && R.seq + PA_NS <= C.seqEnd) {              // refill it with the row 9 steps ahead
+    mbarrier_expect_tx(&s_full[PH], PA_IW * 4);
+    tma_load_2d(rowp, map, C.x0 - 8, clampi2(C.ia + R.seq + PA_NS, 0, C.h - 1), &s_full[PH]);
+  }
+  R.seq++;
+  if (!MAIN) return;
+  // -------------------------------------------------------------------- vertical 9-tap -> level-0 row y
+  const int y = R.y;
+  float4 o4;
+  {
+    // window order: oldest = slot PH+1 (row y-4) ... newest = slot PH (row y+4); same sums as pa_sym9, two columns at once
+#define PAW(i, hh) W[(PH + 1 + (i)) % 9][hh]
+#define PAV(hh)                                                                                             \
+  fma2(pk2(lp.k[0], lp.k[0]), add2(PAW(0, hh), PAW(8, hh)),                                                  \
+       fma2(pk2(lp.k[1], lp.k[1]), add2(PAW(1, hh), PAW(7, hh)),                                             \
+            fma2(pk2(lp.k[2], lp.k[2]), add2(PAW(2, hh), PAW(6, hh)),                                        \
+                 fma2(pk2(lp.k[4], lp.k[4]), PAW(4, hh), mul2(pk2(lp.k[3], lp.k[3]), add2(PAW(3, hh), PAW(5, hh)))))))
+    const float2 lo = upk(PAV(0)), hi = upk(PAV(1));
 #undef PAV
 #undef PAW
-    if (C.own && y >= C.R0 && y < C.R1) {
-      float *out = C.lev0 + (size_t)y * C.p0 + C.cb;
-      if (C.cb + 3 < C.w) *reinterpret_cast<float4 *>(out) = o;
-      else {
-        if (C.cb < C.w) out[0] = o.x;
-        if (C.cb + 1 < C.w) out[1] = o.y;
-        if (C.cb + 2 < C.w) out[2] = o.z;
-      }
+    o4 = make_float4(lo.x, lo.y, hi.x, hi.y);
+  }
+  if (C.own && y >= C.R0 && y < C.R1) {
+    if (!EDGE || C.cb + 3 < C.w) *reinterpret_cast<float4 *>(R.out0) = o4;
+    else {
+      if (C.cb < C.w) R.out0[0] = o4.x;
+      if (C.cb + 1 < C.w) R.out0[1] = o4.y;
+      if (C.cb + 2 < C.w) R.out0[2] = o4.z;
     }
-    if (C.sd) *reinterpret_cast<float4 *>(&s_l0[y & 1][4 * t]) = o;
   }
-  __syncthreads();
-  if (t == 0 && u + PA_NS <= C.ib) {                        // refill the slot of row u (u <= ib holds then)
-    const int slot = (u - C.ia) & (PA_NS - 1);
-    mbarrier_expect_tx(&s_full[slot], PA_IW * 4);
-    tma_load_2d(&s_in[slot][0], map, C.x0 - 8, u + PA_NS, &s_full[slot]);
+  R.out0 += C.p0;
+  R.y = y + 1;
+  if (!C.sd) return;
+  // -------------------------------------------------------------------- ScaleDown: horizontal 5-tap of row y
+  float a[7];                                                // columns cb-2 .. cb+4
+  if (!EDGE) {
+    a[0] = __shfl_up_sync(0xffffffffu, o4.z, 1);
+    a[1] = __shfl_up_sync(0xffffffffu, o4.w, 1);
+    a[2] = o4.x; a[3] = o4.y; a[4] = o4.z; a[5] = o4.w;
+    a[6] = __shfl_down_sync(0xffffffffu, o4.x, 1);
+  } else {
+    __syncwarp();                                            // the previous row's reads are done
+    *reinterpret_cast<float4 *>(s_l0 + 4 * lane) = o4;       // s_l0[i] = column x0-4+i
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 7; i++) a[i] = s_l0[clampi2(clampi2(C.cb - 2 + i, 0, C.w - 1) - (C.x0 - 4), 0, 4 * PA_THREADS - 1)];
   }
-  if (C.sd && row) {
+  float2 *h2 = s_h2 + lane;                                  // [row & 7][lane] and again at [8 + (row & 7)][lane]: a private
+  {                                                          // column, stored twice so that any 5 consecutive rows are contiguous
+    const float2 hv = make_float2(sd_h(sdk, a[0], a[1], a[2], a[3], a[4]), sd_h(sdk, a[2], a[3], a[4], a[5], a[6]));
+    float2 *hw = h2 + (y & 7) * PA_THREADS;
+    hw[0] = hv;
+    hw[8 * PA_THREADS] = hv;
+  }
+  // ---------------------------------------------------------------------- ... vertical 5-tap -> the level-1 row that is complete
+  if (R.nextY1 < C.Y1b && R.trig <= y) {
+    f32x2 q[5];
+    if (y >= 4 && R.trig == 2 * R.nextY1 + 2) {             // rows y-4 .. y, no clamping (y-4 = y+4 mod 8)
+#pragma unroll
+      for (int j = 0; j < 5; j++) q[j] = pk(h2[(((y + 4) & 7) + j) * PA_THREADS]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 5; j++) q[j] = pk(h2[(clampi2(2 * R.nextY1 - 2 + j, 0, C.h - 1) & 7) * PA_THREADS]);
+    }
+    // sd_v on both columns: FMUL(k0,(r0+r4)); FFMA(k2,c); FFMA(k1,(r1+r3))
+    const f32x2 s = fma2(pk2(sdk.k[1], sdk.k[1]), add2(q[1], q[3]),
+                         fma2(pk2(sdk.k[2], sdk.k[2]), q[2], mul2(pk2(sdk.k[0], sdk.k[0]), add2(q[0], q[4]))));
     if (C.own) {
-      // ---------------------------------------------------------------- ScaleDown: horizontal 5-tap of row y
-      float a[7];
-      const float *l0 = s_l0[y & 1];
-      if (!C.edge) {                                        // columns cb-4 .. cb+7: three conflict-free 128-bit loads
-        const float4 *p = reinterpret_cast<const float4 *>(l0 + 4 * t - 4);
-        const float4 q0 = p[0], q1 = p[1], q2 = p[2];
-        a[0] = q0.z; a[1] = q0.w; a[2] = q1.x; a[3] = q1.y; a[4] = q1.z; a[5] = q1.w; a[6] = q2.x;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 7; i++) a[i] = l0[clampi2(C.cb - 2 + i, 0, C.w - 1) - (C.x0 - 4)];
-      }
-      s_h2[y & 7][t] = make_float2(sd_h(sdk, a[0], a[1], a[2], a[3], a[4]), sd_h(sdk, a[2], a[3], a[4], a[5], a[6]));
+      const float2 r = upk(s);
+      if (!EDGE || C.x1 + 1 < C.w1) *reinterpret_cast<float2 *>(R.out1) = r;
+      else if (C.x1 < C.w1) R.out1[0] = r.x;
     }
-    // ------------------------------------------------------------------ ... vertical 5-tap -> level-1 rows that are complete
-    while (nextY1 < C.Y1b && min(2 * nextY1 + 2, C.h - 1) <= y) {
-      if (C.own) {
-        float2 q[5];
-#pragma unroll
-        for (int j = 0; j < 5; j++) q[j] = s_h2[clampi2(2 * nextY1 - 2 + j, 0, C.h - 1) & 7][t];
-        const float ox = sd_v(sdk, q[0].x, q[1].x, q[2].x, q[3].x, q[4].x);
-        const float oy = sd_v(sdk, q[0].y, q[1].y, q[2].y, q[3].y, q[4].y);
-        float *out = C.lev1 + (size_t)nextY1 * C.p1 + C.x1;
-        if (C.x1 + 1 < C.w1) *reinterpret_cast<float2 *>(out) = make_float2(ox, oy);
-        else if (C.x1 < C.w1) out[0] = ox;
-      }
-      nextY1++;
-    }
+    R.out1 += C.p1;
+    R.nextY1++;
+    R.trig = min(2 * R.nextY1 + 2, C.h - 1);
   }
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void pa_march(const PaCtx &C, PaRun &R, const Taps9 &lp, const Taps5 &sdk, float *s_in, float2 *s_h2,
+                                         float *s_l0, uint64_t *s_full, const CUtensorMap *map)
+{
+  f32x2 W[9][2];
+  // the first 8 rows only fill the window (seqEnd >= 8 always)
+#define PA_PRO(p) pa_step<(p), EDGE, false>(C, R, W, lp, sdk, s_in, s_h2, s_l0, s_full, map);
+  PA_PRO(0) PA_PRO(1) PA_PRO(2) PA_PRO(3) PA_PRO(4) PA_PRO(5) PA_PRO(6) PA_PRO(7)
+#undef PA_PRO
+#define PA_STEP(p) { if (R.seq > C.seqEnd) break; pa_step<(p), EDGE, true>(C, R, W, lp, sdk, s_in, s_h2, s_l0, s_full, map); }
+  for (;;) {
+    PA_STEP(8)
+    R.par ^= 1u;                                             // slots 0..7 start their next use
+    PA_STEP(0) PA_STEP(1) PA_STEP(2) PA_STEP(3) PA_STEP(4) PA_STEP(5) PA_STEP(6) PA_STEP(7)
+  }
+#undef PA_STEP
 }
 
 __global__ void __launch_bounds__(PA_THREADS)
 pyr_lowpass_sd_kernel(const __grid_constant__ PyrAParams P)
 {
-  __shared__ __align__(128) float s_in[PA_NS][PA_IW];
-  __shared__ __align__(16) float s_l0[2][PA_IW];               // level-0 row handed to the ScaleDown
-  __shared__ __align__(8) float2 s_h2[8][PA_THREADS];          // [row & 7][thread]: private columns
+  __shared__ __align__(128) float s_in[PA_NS * PA_SLOT];
+  __shared__ __align__(16) float s_l0[4 * PA_THREADS];         // level-0 row of an edge strip (ScaleDown neighbours)
+  __shared__ __align__(8) float2 s_h2[16 * PA_THREADS];        // [row & 7][lane] (+ a second copy 8 rows further): private columns
   __shared__ __align__(8) uint64_t s_full[PA_NS];
 
-  const int t = threadIdx.x;
+  const int lane = threadIdx.x;
   const int strip = blockIdx.x % P.stripsX, rb = blockIdx.x / P.stripsX, img = blockIdx.y;
   PaCtx C;
   C.w = P.w; C.h = P.h;
@@ -172,45 +216,36 @@ pyr_lowpass_sd_kernel(const __grid_constant__ PyrAParams P)
   C.sd = P.lev1 != nullptr;
   const int Y1a = C.R0 >> 1;
   C.Y1b = C.sd ? ((rb == P.rowBlocks - 1) ? P.h1 : min(C.R1 >> 1, P.h1)) : 0;
-  // level-0 rows this CTA computes / input rows it needs
-  C.ya = C.sd ? max(C.R0 - 2, 0) : C.R0;
-  C.yb = C.sd ? min(max(C.R1 - 1, 2 * C.Y1b), C.h - 1) : C.R1 - 1;
-  C.ia = max(C.ya - 4, 0); C.ib = min(C.yb + 4, C.h - 1);
+  // level-0 rows this warp computes: its own rows plus what its level-1 rows need
+  const int ya = C.sd ? max(C.R0 - 2, 0) : C.R0;
+  const int yb = C.sd ? min(max(C.R1 - 1, 2 * C.Y1b), C.h - 1) : C.R1 - 1;
+  C.ia = ya - 4;                                              // input rows ia .. yb+4 (clamped when loaded)
+  C.seqEnd = yb + 4 - C.ia;
   C.p0 = P.p0; C.p1 = P.p1; C.w1 = P.w1;
   const CUtensorMap *map = P.inMaps + img;
-  C.lev0 = P.lev0 + (size_t)img * P.lev0Stride;
-  C.lev1 = C.sd ? P.lev1 + (size_t)img * P.lev1Stride : nullptr;
+  C.cb = C.x0 - 4 + 4 * lane;                                 // level-0 columns cb .. cb+3
+  C.own = lane >= 1 && lane <= 30;                            // owned columns x0 .. x0+119
+  C.x1 = (C.x0 >> 1) + 2 * (lane - 1);                        // this lane's two level-1 columns
+  PaRun R;
+  R.seq = 0; R.y = ya; R.par = 0;
+  R.nextY1 = Y1a; R.trig = min(2 * Y1a + 2, C.h - 1);
+  R.out0 = P.lev0 + (size_t)img * P.lev0Stride + (ptrdiff_t)ya * C.p0 + C.cb;
+  R.out1 = C.sd ? P.lev1 + (size_t)img * P.lev1Stride + (ptrdiff_t)Y1a * C.p1 + C.x1 : nullptr;
 
-  if (t == 0) {
+  if (lane == 0) {
     for (int i = 0; i < PA_NS; i++) mbarrier_init(&s_full[i], 1);
     mbarrier_init_fence();
+    for (int i = 0; i < PA_NS; i++) {                         // the maps are kernel parameters: no descriptor fence needed
+      mbarrier_expect_tx(&s_full[i], PA_IW * 4);
+      tma_load_2d(s_in + i * PA_SLOT, map, C.x0 - 8, clampi2(C.ia + i, 0, C.h - 1), &s_full[i]);
+    }
   }
-  __syncthreads();
-  if (t == 0) {                                             // the maps are kernel parameters: no descriptor fence needed
-    for (int i = 0; i < PA_NS; i++)
-      if (C.ia + i <= C.ib) {
-        mbarrier_expect_tx(&s_full[i], PA_IW * 4);
-        tma_load_2d(&s_in[i][0], map, C.x0 - 8, C.ia + i, &s_full[i]);
-      }
-  }
-  C.edge = (C.x0 == 0) || (C.x0 + PA_IW - 8 > C.w);        // some staged column lies outside the image
-  C.act = t < 62;                                           // level-0 columns cb .. cb+3
-  C.cb = C.x0 - 4 + 4 * t;
-  C.own = t >= 1 && t <= 60;                                // owned columns x0 .. x0+239
-  C.x1 = (C.x0 >> 1) + 2 * (t - 1);                         // this thread's two level-1 columns
-  int nextY1 = Y1a;
+  __syncwarp();
   const Taps9 lp = P.lp;
   const Taps5 sdk = P.sd;
-  float4 W[9];
-#pragma unroll
-  for (int i = 0; i < 9; i++) W[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  const int uend = C.yb + 4;
-#define PA_STEP(p) { const int u = u0 + (p); if (u > uend) break; pa_step<(p)>(C, u, nextY1, W, lp, sdk, s_in, s_l0, s_h2, s_full, map); }
-  for (int u0 = C.ia;; u0 += 9) {
-    PA_STEP(0) PA_STEP(1) PA_STEP(2) PA_STEP(3) PA_STEP(4) PA_STEP(5) PA_STEP(6) PA_STEP(7) PA_STEP(8)
-  }
-#undef PA_STEP
+  const bool edge = (C.x0 == 0) || (C.x0 + PA_IW - 8 > C.w);   // some staged column lies outside the image
+  if (edge) pa_march<true>(C, R, lp, sdk, s_in, s_h2, s_l0, s_full, map);
+  else pa_march<false>(C, R, lp, sdk, s_in, s_h2, s_l0, s_full, map);
 }
 
 const void *pyr_a_func() { return (const void *)pyr_lowpass_sd_kernel; }
