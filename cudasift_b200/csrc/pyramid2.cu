@@ -97,8 +97,12 @@ __device__ __forceinline__ void pa_step(const PaCtx &C, PaRun &R, f32x2 (&W)[9][
   float o[4];
 #pragma unroll
   for (int d = 0; d < 4; d++)
+#ifdef PA_SKEL   // diagnostic build (scripts/expbuild.sh -DPA_SKEL): the march without its arithmetic = the memory-side ceiling
+    o[d] = v[d + 4];
+#else
     o[d] = pa_sym9(lp, v[d + 4], __fadd_rn(v[d + 5], v[d + 3]), __fadd_rn(v[d + 6], v[d + 2]),
                    __fadd_rn(v[d + 7], v[d + 1]), __fadd_rn(v[d + 8], v[d]));
+#endif
   W[PH][0] = pk2(o[0], o[1]);
   W[PH][1] = pk2(o[2], o[3]);
   __syncwarp();                                              // every lane has consumed the slot
@@ -119,7 +123,11 @@ __device__ __forceinline__ void pa_step(const PaCtx &C, PaRun &R, f32x2 (&W)[9][
        fma2(pk2(lp.k[1], lp.k[1]), add2(PAW(1, hh), PAW(7, hh)),                                             \
             fma2(pk2(lp.k[2], lp.k[2]), add2(PAW(2, hh), PAW(6, hh)),                                        \
                  fma2(pk2(lp.k[4], lp.k[4]), PAW(4, hh), mul2(pk2(lp.k[3], lp.k[3]), add2(PAW(3, hh), PAW(5, hh)))))))
+#ifdef PA_SKEL
+    const float2 lo = upk(PAW(4, 0)), hi = upk(PAW(4, 1));
+#else
     const float2 lo = upk(PAV(0)), hi = upk(PAV(1));
+#endif
 #undef PAV
 #undef PAW
     o4 = make_float4(lo.x, lo.y, hi.x, hi.y);
@@ -151,7 +159,11 @@ __device__ __forceinline__ void pa_step(const PaCtx &C, PaRun &R, f32x2 (&W)[9][
   }
   float2 *h2 = s_h2 + lane;                                  // [row & 7][lane] and again at [8 + (row & 7)][lane]: a private
   {                                                          // column, stored twice so that any 5 consecutive rows are contiguous
+#ifdef PA_SKEL
+    const float2 hv = make_float2(a[2] + a[0] + a[6], a[4]);
+#else
     const float2 hv = make_float2(sd_h(sdk, a[0], a[1], a[2], a[3], a[4]), sd_h(sdk, a[2], a[3], a[4], a[5], a[6]));
+#endif
     float2 *hw = h2 + (y & 7) * PA_THREADS;
     hw[0] = hv;
     hw[8 * PA_THREADS] = hv;
@@ -198,7 +210,10 @@ __device__ __forceinline__ void pa_march(const PaCtx &C, PaRun &R, const Taps9 &
 #undef PA_STEP
 }
 
-__global__ void __launch_bounds__(PA_THREADS)
+#ifndef PA_MINB
+#define PA_MINB 1
+#endif
+__global__ void __launch_bounds__(PA_THREADS, PA_MINB)
 pyr_lowpass_sd_kernel(const __grid_constant__ PyrAParams P)
 {
   __shared__ __align__(128) float s_in[PA_NS * PA_SLOT];
