@@ -1,6 +1,8 @@
 """Build recipes for cudasift_b200 (no build system: plain nvcc / gcc command lines).
 
 build_library()  -> cudasift_b200/lib/libcudasift_b200.so   (the product, sm_100a only)
+build_library(managed=True) -> cudasift_b200/lib/libcudasift_b200_managed.so  (the MANAGEDMEM flavour of the API,
+                    cudaSift.h:35-40: SiftData::m_data in unified memory)
 build_oracle()   -> oracle/liboracle.so                      (CPU checker, test infrastructure)
 build_reference()-> oracle/_ref/libcudasift_ref.so           (the unmodified reference, compiled
                     from /root/reference where it lies; only possible in the build container)
@@ -50,23 +52,42 @@ def nvcc_path():
     return None
 
 
-def build_library(force=False, verbose=False):
+LIB_MANAGED = os.path.join(LIBDIR, "libcudasift_b200_managed.so")
+MANAGED_UNITS = ("api.cu", "homography.cu", "geom.cu")     # the translation units that look at MANAGEDMEM
+OBJDIR = os.path.join(LIBDIR, "obj")
+
+
+def build_library(force=False, verbose=False, managed=False):
+    """Every translation unit to its own object (in parallel, rebuilt when a source or header is newer), one link."""
+    from concurrent.futures import ThreadPoolExecutor
+    lib = LIB_MANAGED if managed else LIB
     srcs = [os.path.join(CSRC, s) for s in SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("common.cuh", "tma.cuh", "pipeline2.h")] + [
+    hdrs = [os.path.join(CSRC, h) for h in ("common.cuh", "tma.cuh", "pipeline2.h")] + [
         os.path.join(ROOT, "include", h) for h in ("cudaSift.h", "cudaImage.h", "cudasift_b200.h")]
-    if not force and _newer(LIB, deps):
-        return LIB
+    if not force and _newer(lib, srcs + hdrs):
+        return lib
     nvcc = nvcc_path()
     if nvcc is None:
-        if os.path.exists(LIB):
-            return LIB   # GPU box without a toolkit: use the prebuilt library that travelled
-        raise RuntimeError("nvcc not found and no prebuilt libcudasift_b200.so")
-    os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + srcs + ["-o", LIB]
-    out = _run(cmd)
-    if verbose:
-        print(out)
-    return LIB
+        if os.path.exists(lib):
+            return lib   # GPU box without a toolkit: use the prebuilt library that travelled
+        raise RuntimeError("nvcc not found and no prebuilt " + os.path.basename(lib))
+    os.makedirs(OBJDIR, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+
+    def compile_unit(name):
+        tag = "_managed" if managed and name in MANAGED_UNITS else ""
+        obj = os.path.join(OBJDIR, name.replace(".cu", tag + ".o"))
+        src = os.path.join(CSRC, name)
+        if force or not _newer(obj, [src] + hdrs):
+            out = _run([nvcc] + flags + (["-DMANAGEDMEM"] if tag else []) + ["-c", src, "-o", obj])
+            if verbose:
+                print(out)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 4)) as ex:
+        objs = list(ex.map(compile_unit, SOURCES))
+    _run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared"] + objs + ["-o", lib])
+    return lib
 
 
 def build_oracle(force=False):
@@ -102,23 +123,30 @@ def build_reference(force=False):
 
 
 DEMO = os.path.join(LIBDIR, "sift_demo")
+DEMO_MANAGED = os.path.join(LIBDIR, "sift_demo_managed")
 
 
-def build_demo(force=False):
-    """examples/sift_demo.cpp: a plain g++ caller of the drop-in headers, linked against the library."""
+def build_demo(force=False, managed=False):
+    """examples/sift_demo.cpp: a plain g++ caller of the drop-in headers, linked against the library
+    (managed=True: compiled with -DMANAGEDMEM against the unified-memory flavour)."""
     src = os.path.join(ROOT, "examples", "sift_demo.cpp")
-    lib = build_library()
-    if not force and _newer(DEMO, [src, lib]):
-        return DEMO
+    lib = build_library(managed=managed)
+    demo = DEMO_MANAGED if managed else DEMO
+    if not force and _newer(demo, [src, lib]):
+        return demo
     if shutil.which("g++") is None:
-        return DEMO if os.path.exists(DEMO) else None
-    _run(["g++", "-O2", "-std=c++17", "-Wall", "-I" + os.path.join(ROOT, "include"), src, "-L" + LIBDIR,
-          "-lcudasift_b200", "-Wl,-rpath,$ORIGIN", "-o", DEMO])
-    return DEMO
+        return demo if os.path.exists(demo) else None
+    _run(["g++", "-O2", "-std=c++17", "-Wall"] + (["-DMANAGEDMEM"] if managed else []) +
+         ["-I" + os.path.join(ROOT, "include"), src, "-L" + LIBDIR,
+          "-lcudasift_b200_managed" if managed else "-lcudasift_b200", "-lz", "-Wl,-rpath,$ORIGIN", "-o", demo])
+    return demo
 
 
 def build_all(force=False, verbose=False):
-    return build_library(force, verbose), build_oracle(force), build_reference(force), build_demo(force)
+    out = build_library(force, verbose), build_oracle(force), build_reference(force), build_demo(force)
+    build_library(force, verbose, managed=True)
+    build_demo(force, managed=True)
+    return out
 
 
 if __name__ == "__main__":

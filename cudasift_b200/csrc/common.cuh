@@ -15,7 +15,11 @@
 #define CS_MAX_LEVELS 8                    // d_PointCounter[8*2+1], cudaSiftD.cu:14
 
 static_assert(sizeof(SiftPoint) == 576, "SiftPoint layout is ABI");
+#ifdef MANAGEDMEM
+static_assert(sizeof(SiftData) == 16, "SiftData layout is ABI (MANAGEDMEM flavour: numPts, maxPts, m_data)");
+#else
 static_assert(sizeof(SiftData) == 24, "SiftData layout is ABI");
+#endif
 static_assert(sizeof(CudaImage) == 48, "CudaImage layout is ABI");
 
 namespace cs {

@@ -1,14 +1,19 @@
 // sift_demo.cpp -- two-view demo written against the drop-in headers only.
 //
 // Plays the role of the reference's mainSift.cpp (main at :25-93, PrintMatchData at :150-200)
-// without OpenCV: 8-bit PGM (P5) in, optional PGM with the match vectors drawn out.  It is a
-// caller of the public API (cudaSift.h / cudaImage.h), nothing here is on the hot path.
+// without OpenCV: 8-bit PGM (P5) or PNG (8-bit grey / RGB / RGBA, decoded here with zlib) in, optional PGM with the
+// matches drawn out.  It is a caller of the public API (cudaSift.h / cudaImage.h), nothing here is on the hot path.
 //
-//   sift_demo left.pgm right.pgm [--thresh T] [--octaves N] [--repeat R] [--device D]
-//             [--ransac LOOPS] [--out marked.pgm] [--print K]
+//   sift_demo left.{pgm,png} right.{pgm,png} [--thresh T] [--octaves N] [--repeat R] [--device D]
+//             [--ransac LOOPS] [--out marked.pgm] [--style marks|reference] [--print K]
+//
+// --style reference draws what the reference's PrintMatchData draws (mainSift.cpp:150-200): a line to the matched
+// feature for matches within 5 px of the homography, and a black-and-white cross of half-length 1.41*scale per feature.
+// Compiled with -DMANAGEDMEM (against libcudasift_b200_managed.so) it exercises the unified-memory flavour of the
+// API (cudaSift.h:35-40, SiftData::m_data).
 //
 // Build (cudasift_b200/build.py: build_demo):
-//   g++ -O2 -Iinclude examples/sift_demo.cpp -Lcudasift_b200/lib -lcudasift_b200 -o sift_demo
+//   g++ -O2 -Iinclude examples/sift_demo.cpp -Lcudasift_b200/lib -lcudasift_b200 -lz -o sift_demo
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -18,7 +23,15 @@
 #include <string>
 #include <vector>
 
+#include <zlib.h>
+
 #include "cudaSift.h"
+
+#ifdef MANAGEDMEM
+#define HOST_POINTS(d) ((d).m_data)
+#else
+#define HOST_POINTS(d) ((d).h_data)
+#endif
 
 namespace {
 
@@ -63,6 +76,76 @@ bool read_pgm(const char *path, GrayImage *img)
   return ok;
 }
 
+// Minimal PNG reader: 8 bits per channel, colour types 0 (grey), 2 (RGB), 4 (grey+alpha), 6 (RGBA), non-interlaced.
+// Colour goes to grey with the weights of cv::cvtColor(BGR2GRAY): (9798 R + 19235 G + 3735 B + 16384) >> 15
+// (mainSift.cpp:37 reads its PNGs with cv::imread(.., 0)).
+bool read_png(const char *path, GrayImage *img)
+{
+  FILE *f = fopen(path, "rb");
+  if (!f) { fprintf(stderr, "cannot open %s\n", path); return false; }
+  std::vector<unsigned char> file;
+  unsigned char buf[65536];
+  size_t n;
+  while ((n = fread(buf, 1, sizeof buf, f)) > 0) file.insert(file.end(), buf, buf + n);
+  fclose(f);
+  static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', '\r', '\n', 0x1a, '\n'};
+  if (file.size() < 33 || memcmp(file.data(), sig, 8) != 0) { fprintf(stderr, "%s: not a PNG\n", path); return false; }
+  auto be32 = [&](size_t o) { return ((unsigned)file[o] << 24) | ((unsigned)file[o + 1] << 16) | ((unsigned)file[o + 2] << 8) | file[o + 3]; };
+  int depth = 0, ctype = 0, interlace = 0;
+  std::vector<unsigned char> idat;
+  for (size_t o = 8; o + 12 <= file.size();) {
+    const size_t len = be32(o);
+    if (o + 12 + len > file.size()) break;
+    const char *type = (const char *)&file[o + 4];
+    if (!memcmp(type, "IHDR", 4) && len >= 13) {
+      img->w = (int)be32(o + 8); img->h = (int)be32(o + 12);
+      depth = file[o + 16]; ctype = file[o + 17]; interlace = file[o + 20];
+    } else if (!memcmp(type, "IDAT", 4)) idat.insert(idat.end(), file.begin() + o + 8, file.begin() + o + 8 + len);
+    else if (!memcmp(type, "IEND", 4)) break;
+    o += 12 + len;
+  }
+  const int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
+  if (depth != 8 || ch == 0 || interlace != 0 || img->w < 1 || img->h < 1) {
+    fprintf(stderr, "%s: unsupported PNG (need 8-bit grey/RGB/RGBA, non-interlaced)\n", path);
+    return false;
+  }
+  const size_t stride = (size_t)img->w * ch;
+  std::vector<unsigned char> raw((stride + 1) * img->h);
+  uLongf rawLen = (uLongf)raw.size();
+  if (uncompress(raw.data(), &rawLen, idat.data(), (uLong)idat.size()) != Z_OK || rawLen != raw.size()) {
+    fprintf(stderr, "%s: corrupt PNG data\n", path);
+    return false;
+  }
+  std::vector<unsigned char> prev(stride, 0), cur(stride);
+  img->px.resize((size_t)img->w * img->h);
+  for (int y = 0; y < img->h; y++) {
+    const unsigned char *line = &raw[(stride + 1) * y];
+    const int filter = line[0];
+    for (size_t i = 0; i < stride; i++) {
+      const int a = i >= (size_t)ch ? cur[i - ch] : 0, b = prev[i], c = i >= (size_t)ch ? prev[i - ch] : 0;
+      int pred = 0;
+      if (filter == 1) pred = a;
+      else if (filter == 2) pred = b;
+      else if (filter == 3) pred = (a + b) >> 1;
+      else if (filter == 4) { const int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c); pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c); }
+      cur[i] = (unsigned char)(line[1 + i] + pred);
+    }
+    for (int x = 0; x < img->w; x++) {
+      const unsigned char *q = &cur[(size_t)x * ch];
+      img->px[(size_t)y * img->w + x] = ch <= 2 ? (float)q[0] : (float)((9798 * q[0] + 19235 * q[1] + 3735 * q[2] + 16384) >> 15);
+    }
+    prev.swap(cur);
+  }
+  return true;
+}
+
+bool read_image(const char *path, GrayImage *img)
+{
+  const size_t n = strlen(path);
+  if (n > 4 && (!strcmp(path + n - 4, ".png") || !strcmp(path + n - 4, ".PNG"))) return read_png(path, img);
+  return read_pgm(path, img);
+}
+
 bool write_pgm(const char *path, const GrayImage &img)
 {
   FILE *f = fopen(path, "wb");
@@ -90,12 +173,35 @@ void draw_segment(GrayImage *img, float x0, float y0, float x1, float y1, float 
 void mark_features(GrayImage *img, const SiftData &d)
 {
   for (int i = 0; i < d.numPts; i++) {
-    const SiftPoint &p = d.h_data[i];
+    const SiftPoint &p = HOST_POINTS(d)[i];
     float r = 2.0f * p.scale, a = p.orientation * 3.14159265f / 180.0f;
     float cx = r * std::cos(a), cy = r * std::sin(a);
     draw_segment(img, p.xpos - cx, p.ypos - cy, p.xpos + cx, p.ypos + cy, 255.0f);
     draw_segment(img, p.xpos + cy, p.ypos - cx, p.xpos - cy, p.ypos + cx, 0.0f);
     if (p.match >= 0 && p.match_error < 5.0f) draw_segment(img, p.xpos, p.ypos, p.match_xpos, p.match_ypos, 255.0f);
+  }
+}
+
+// What the reference's PrintMatchData draws (mainSift.cpp:150-200), with every write bounds-checked: for matches whose
+// match_error is below 5 px a white line from the feature towards the matched feature's position in the other image,
+// and for every feature a black cross offset by (+1,+1) under a white cross, arms of min(distance to the border,
+// (int)(1.41 * scale)) pixels.
+void draw_like_reference(GrayImage *img, const SiftData &d1, const SiftData &d2)
+{
+  const SiftPoint *a = HOST_POINTS(d1), *b = HOST_POINTS(d2);
+  const int w = img->w, h = img->h;
+  auto put = [&](int x, int y, float v) { if (x >= 0 && y >= 0 && x < w && y < h) img->px[(size_t)y * w + x] = v; };
+  for (int j = 0; j < d1.numPts; j++) {
+    const int k = a[j].match;
+    if (k >= 0 && k < d2.numPts && a[j].match_error < 5.0f) {
+      const float dx = b[k].xpos - a[j].xpos, dy = b[k].ypos - a[j].ypos;
+      const int len = (int)std::max(std::fabs(dx), std::fabs(dy));
+      for (int l = 0; l < len; l++) put((int)(a[j].xpos + dx * l / len), (int)(a[j].ypos + dy * l / len), 255.0f);
+    }
+    const int x = (int)(a[j].xpos + 0.5f), y = (int)(a[j].ypos + 0.5f);
+    const int s = std::min(std::min(x, y), std::min(std::min(w - x - 2, h - y - 2), (int)(1.41f * a[j].scale)));
+    for (int t = 0; t < s; t++) { put(x + 1 - t, y + 1, 0.0f); put(x + 1 + t, y + 1, 0.0f); put(x + 1, y + 1 - t, 0.0f); put(x + 1, y + 1 + t, 0.0f); }
+    for (int t = 0; t < s; t++) { put(x - t, y, 255.0f); put(x + t, y, 255.0f); put(x, y - t, 255.0f); put(x, y + t, 255.0f); }
   }
 }
 
@@ -116,8 +222,8 @@ double now_ms()
 int main(int argc, char **argv)
 {
   if (argc < 3) {
-    fprintf(stderr, "usage: %s left.pgm right.pgm [--thresh T] [--octaves N] [--repeat R] [--device D] "
-                    "[--ransac LOOPS] [--out marked.pgm] [--print K]\n", argv[0]);
+    fprintf(stderr, "usage: %s left.{pgm,png} right.{pgm,png} [--thresh T] [--octaves N] [--repeat R] [--device D] "
+                    "[--ransac LOOPS] [--out marked.pgm] [--style marks|reference] [--print K]\n", argv[0]);
     return 2;
   }
   const float thresh = (float)atof(arg_value(argc, argv, "--thresh", "3.0"));
@@ -127,10 +233,11 @@ int main(int argc, char **argv)
   const int ransac = atoi(arg_value(argc, argv, "--ransac", "10000"));
   const int nprint = atoi(arg_value(argc, argv, "--print", "0"));
   const char *out = arg_value(argc, argv, "--out", "");
+  const char *style = arg_value(argc, argv, "--style", "marks");
   const float initBlur = 1.0f;
 
   GrayImage left, right;
-  if (!read_pgm(argv[1], &left) || !read_pgm(argv[2], &right)) return 1;
+  if (!read_image(argv[1], &left) || !read_image(argv[2], &right)) return 1;
   if (left.w != right.w || left.h != right.h) { fprintf(stderr, "image sizes differ\n"); return 1; }
   printf("Image size = (%d,%d)\n", left.w, left.h);
 
@@ -167,12 +274,13 @@ int main(int argc, char **argv)
   for (int i = 0; i < 9; i++) printf("%s%.6g", i % 3 == 0 ? "\n  " : " ", homography[i]);
   printf("\n");
   for (int i = 0; i < std::min(nprint, sift1.numPts); i++) {
-    const SiftPoint &p = sift1.h_data[i];
+    const SiftPoint &p = HOST_POINTS(sift1)[i];
     printf("%5d: (%7.2f,%7.2f) scale %5.2f ori %6.1f -> %5d (%7.2f,%7.2f) score %.4f ambiguity %.4f error %.2f\n", i,
            p.xpos, p.ypos, p.scale, p.orientation, p.match, p.match_xpos, p.match_ypos, p.score, p.ambiguity, p.match_error);
   }
   if (out[0]) {
-    mark_features(&left, sift1);
+    if (!strcmp(style, "reference")) draw_like_reference(&left, sift1, sift2);
+    else mark_features(&left, sift1);
     if (!write_pgm(out, left)) { fprintf(stderr, "cannot write %s\n", out); return 1; }
     printf("Wrote %s\n", out);
   }

@@ -43,6 +43,15 @@ def test_library_exports_reference_cxx_api():
     assert not missing, "reference API symbols not exported: %s" % sorted(missing)
 
 
+def test_managed_flavour_exports_the_same_api():
+    """cudaSift.h:27-32 (MANAGEDMEM): the unified-memory flavour is a second library with the same mangled symbols."""
+    lib = build.build_library(managed=True)
+    out = subprocess.run(["nm", "-D", "--defined-only", lib], stdout=subprocess.PIPE, text=True).stdout
+    syms = {line.split()[-1] for line in out.splitlines() if line.strip()}
+    assert not (set(MANGLED) - syms)
+    assert os.path.exists(build.build_demo(managed=True))
+
+
 def test_struct_layouts():
     assert cs.SIFT_DTYPE.itemsize == 576
     assert cs.SIFT_DTYPE.fields["data"][1] == 64 and cs.SIFT_DTYPE.fields["match"][1] == 32

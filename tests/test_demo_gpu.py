@@ -46,3 +46,53 @@ def test_demo_program(cs, tmp_path):
     with open(out, "rb") as f:
         assert f.read(2) == b"P5"
     assert os.path.getsize(out) > 1280 * 960
+
+
+def _run_demo(demo, args):
+    r = subprocess.run([demo] + args, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
+    assert r.returncode == 0, r.stdout
+    m = re.search(r"Number of original features: (\d+) (\d+)", r.stdout)
+    f = re.search(r"Number of matching features: (\d+) (\d+)", r.stdout)
+    return (int(m.group(1)), int(m.group(2))), (int(f.group(1)), int(f.group(2))), r.stdout
+
+
+@pytest.mark.gpu
+def test_demo_png_input_and_reference_drawing(cs, tmp_path):
+    """the reference demo's second input pair is PNG (mainSift.cpp:37-38) and its output is the drawing of
+    PrintMatchData (mainSift.cpp:150-200).  The demo decodes PNG itself (zlib) and --style reference draws the same
+    primitives; feature counts must equal the ctypes API on the identically converted grey image."""
+    cv2 = pytest.importorskip("cv2")
+    p1 = os.path.join(ROOT, "oracle", "_ref", "data", "img1.png")
+    p2 = os.path.join(ROOT, "oracle", "_ref", "data", "img2.png")
+    if not (os.path.exists(p1) and os.path.exists(p2)):
+        pytest.skip("oracle/_ref/data/img1.png, img2.png did not travel (built only where /root/reference exists)")
+    demo = _build.build_demo()
+    out = str(tmp_path / "drawn.pgm")
+    (n1, n2), (fit, matches), log = _run_demo(demo, [p1, p2, "--thresh", "2.0", "--repeat", "1", "--out", out, "--style", "reference"])
+    g1 = cv2.cvtColor(cv2.imread(p1, cv2.IMREAD_COLOR), cv2.COLOR_BGR2GRAY).astype(np.float32)
+    g2 = cv2.cvtColor(cv2.imread(p2, cv2.IMREAD_COLOR), cv2.COLOR_BGR2GRAY).astype(np.float32)
+    assert n1 == len(cs.extract_host(g1, thresh=2.0)) and n2 == len(cs.extract_host(g2, thresh=2.0)), log
+    assert matches > 100 and fit > 100, log                      # the pair overlaps (README.md:33 reports ~1000+ matches)
+    with open(out, "rb") as f:
+        hdr = f.readline() + f.readline() + f.readline()
+        drawn = np.frombuffer(f.read(), np.uint8).reshape(g1.shape)
+    assert hdr.startswith(b"P5")
+    changed = int((drawn != np.clip(g1, 0, 255).astype(np.uint8)).sum())
+    assert changed > 20 * n1 // 4, changed                        # crosses and match lines were drawn
+
+
+@pytest.mark.gpu
+def test_demo_managed_memory_flavour(cs, tmp_path):
+    """SURVEY 8 f4 / cudaSift.h:27-32: the MANAGEDMEM flavour (SiftData::m_data in unified memory) is built
+    (libcudasift_b200_managed.so + the demo compiled with -DMANAGEDMEM) and gives the same counts as the default build."""
+    demo, demo_m = _build.build_demo(), _build.build_demo(managed=True)
+    assert demo_m and os.path.exists(demo_m)
+    left = synth_image(960, 720, seed=8)
+    right = np.roll(left, (5, 7), axis=(0, 1))
+    _write_pgm(str(tmp_path / "l.pgm"), left)
+    _write_pgm(str(tmp_path / "r.pgm"), right)
+    args = [str(tmp_path / "l.pgm"), str(tmp_path / "r.pgm"), "--thresh", "3.0", "--repeat", "2", "--print", "1"]
+    c0, f0, log0 = _run_demo(demo, args)
+    c1, f1, log1 = _run_demo(demo_m, args)
+    assert c0 == c1, (log0, log1)
+    assert f1[0] > 50 and abs(f1[0] - f0[0]) <= max(3, f0[0] // 50), (f0, f1)     # RANSAC draws depend on record order
