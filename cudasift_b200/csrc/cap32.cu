@@ -1,8 +1,8 @@
 // cap32.cu -- the reference's cap of 32 extrema per (30x8 block, scale) (quirk of FindPointsMultiNew,
 // cudaSiftD.cu:1361-1380: `pos<MEMWID` keeps the first 32 in (column, row) order, `tx<totbits` refines them).
 //
-// The detector (detect2.cu) counts the extrema of every such cell in packed 8-bit counters and lists the cells
-// that received a 33rd.  That almost never happens (it needs > 13 % of a block's pixels to be 26-neighbour extrema
+// The detector (detect2.cu) counts the extrema of every such cell in packed 8-bit counters (reductions without a
+// return value); this kernel scans the counters for cells past the limit.  That almost never happens (it needs > 13 % of a block's pixels to be 26-neighbour extrema
 // above the threshold), so the repair is a separate, tiny, usually empty kernel: per listed cell it recomputes the
 // cell's DoG planes from the octave base image with the detector's arithmetic, ranks the extrema in the reference's
 // order and deletes the keypoints of rank >= 32 from the image's list (those that survived refinement; the list is
@@ -31,7 +31,29 @@ cap32_fixup_kernel(const __grid_constant__ Detect2Params P)
 {
   const int img = blockIdx.x, tid = threadIdx.x;
   unsigned int *counters = P.counters + (size_t)img * CS_CNT_STRIDE;
-  const int novf = (int)min(counters[3], (unsigned)CS_OVF_MAX);
+  // the cells that received more than capLimit extrema: scan the image's packed 8-bit counters (the detector only
+  // counts, with fire-and-forget reductions)
+  __shared__ int s_novf;
+  __shared__ unsigned int s_ovf[CS_OVF_MAX];
+  if (tid == 0) s_novf = 0;
+  __syncthreads();
+  {
+    const unsigned int *cells = P.cells + (size_t)img * P.cellWords;
+    const unsigned lim = (unsigned)P.capLimit;
+    for (int i = tid; i < P.cellWords; i += C32_THREADS) {
+      const unsigned v = __ldg(cells + i);
+      if (v == 0) continue;
+#pragma unroll
+      for (int b = 0; b < 4; b++)
+        if (((v >> (8 * b)) & 0xff) > lim) {
+          const int at = atomicAdd(&s_novf, 1);
+          if (at < CS_OVF_MAX) s_ovf[at] = (unsigned)(4 * i + b);
+        }
+    }
+  }
+  __syncthreads();
+  const int novf = min(s_novf, CS_OVF_MAX);
+  if (tid == 0) counters[3] = (unsigned)s_novf;          // diagnostics: cells past the limit
   if (novf == 0) return;
 
   __shared__ float s_v[4][C32_H][C32_VW];
@@ -45,7 +67,7 @@ cap32_fixup_kernel(const __grid_constant__ Detect2Params P)
   __syncthreads();
 
   for (int oi = 0; oi < novf; oi++) {
-    const int cell = (int)P.ovf[(size_t)img * CS_OVF_MAX + oi];
+    const int cell = (int)s_ovf[oi];
     int level = 0;
     for (int l = 1; l < CS_MAX_LEVELS; l++)
       if (P.lev[l].w > 0 && cell >= P.cellBase[l]) level = l;

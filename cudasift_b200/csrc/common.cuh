@@ -152,6 +152,7 @@ struct Detect2Params {
   int levPitch[CS_MAX_LEVELS];
 };
 int launch_detect2(const Detect2Params &p, int sms, cudaStream_t st);
+int detect2_init_device();   // fills the device-side pow table (once per device; not inside a stream capture)
 int launch_cap32_fixup(const Detect2Params &p, int batch, cudaStream_t st);
 #define CS_D2_STRIP 244       // tested columns per detector strip (multiple of 4: TMA box alignment)
 

@@ -86,6 +86,16 @@ __device__ __forceinline__ void d2_vertical(f32x2 (&W0)[9], f32x2 (&W1)[9], f32x
 
 struct D2Keypoint { float x, y, scale, sharpness, edgeness, subsampling; unsigned int tag; };
 
+// powf(2.0f, scale / 5) of cudaSiftD.cu:1413 for the five scales an extremum can have.  The table is filled on the
+// device by the same powf (d2_fill_pow_table, first launch per device), so the values are the ones the reference's
+// expression yields; it takes ~100 instructions out of the refinement of every extremum.
+__device__ float d2_pow_table[CS_NUM_SCALES];
+__device__ __forceinline__ float d2_pow_scale(int scale) { return d2_pow_table[scale]; }
+__global__ void d2_fill_pow_table()
+{
+  if (threadIdx.x < CS_NUM_SCALES) d2_pow_table[threadIdx.x] = powf(2.0f, __fdiv_rn((float)threadIdx.x, (float)CS_NUM_SCALES));
+}
+
 __device__ __forceinline__ void d2_store_keypoint(SiftPoint *pts, int maxPts, unsigned int idx, const D2Keypoint &kp)
 {
   if (idx >= (unsigned)maxPts) idx = maxPts - 1;    // cudaSiftD.cu:1421
@@ -137,7 +147,7 @@ __device__ __forceinline__ void d2_refine(const float (&v)[3][3][3], int gx, int
     pds = __fdividef(ds, dss);
   }
   float dsum = __fmaf_rn(ds, pds, __fmaf_rn(dx, pdx, __fmul_rn(dy, pdy)));
-  float sc = __fmul_rn(powf(2.0f, __fdiv_rn((float)scale, (float)CS_NUM_SCALES)), exp2f(__fmul_rn(pds, factor)));
+  float sc = __fmul_rn(d2_pow_scale(scale), exp2f(__fmul_rn(pds, factor)));
   if (!(sc >= lowestScale)) return;
   D2Keypoint kp;
   kp.x = __fadd_rn((float)gx, pdx);
@@ -378,12 +388,9 @@ detect2_kernel(const __grid_constant__ Detect2Params P)
             const unsigned int tag = (unsigned)gx | ((unsigned)gy << 13) | ((unsigned)(p - 1) << 26) | ((unsigned)level << 29);
             if (P.cells) {                                // extrema per 30x8 block and scale (reference cap, cudaSiftD.cu:1371)
               const int cell = P.cellBase[level] + ((gy >> 3) * P.cellsX[level] + gx / 30) * CS_NUM_SCALES + (p - 1);
-              unsigned int *cw = P.cells + (size_t)img * P.cellWords + (cell >> 2);
-              const unsigned old = atomicAdd(cw, 1u << (8 * (cell & 3)));
-              if (((old >> (8 * (cell & 3))) & 0xff) == (unsigned)P.capLimit) {      // the 33rd extremum of this cell
-                const unsigned at = atomicAdd(&counters[3], 1u);
-                if (at < CS_OVF_MAX) P.ovf[(size_t)img * CS_OVF_MAX + at] = (unsigned)cell;
-              }
+              // no return value -> RED: the count is not on this thread's critical path; the fix-up kernel finds the
+              // cells that went past the limit by scanning the counters
+              atomicAdd(P.cells + (size_t)img * P.cellWords + (cell >> 2), 1u << (8 * (cell & 3)));
             }
             d2_refine(v, gx, gy, p - 1, L.subsampling, L.lowestScale, P.edgeLimit, P.factor, tag, s_kq, &s_kn, pts,
                       &counters[0], P.maxPts);
@@ -410,11 +417,17 @@ detect2_kernel(const __grid_constant__ Detect2Params P)
 // The producers run ahead of the consumers through three vertical-result buffers (buffer = group); hand-over is by
 // named barriers (bar.arrive / bar.sync) instead of CTA-wide barriers:
 //   FULL[g]  producers -> group g: v[g] written        EMPTY[g] group g -> producers: v[g] is in registers
-//   DONE[g]  group g -> producers: its step (DoG row, candidate list, extrema tests) is complete; the producers check
-//            it three steps later, just before they signal FULL of the group's next step.  Hence, when a group
-//            passes FULL of step k, every step <= k-3 of every group is complete: it may test the extrema of row k-4
-//            (rows k-5..k-3) and overwrite ring slot k mod 8 (last read for row k-7).
+//   DONE[g]  group g -> producers: the DoG row and the candidate list of its step are written (the extrema tests of
+//            an older row follow, off the producers' critical path)
+//   LATE[g]  group g -> producers: its previous step is complete, tests included (signalled at the start of the next step)
+//            The producers check DONE of step m-3 and LATE of step m-4 just before they signal FULL of step m.  Hence,
+//            when a group passes FULL of step k, every DoG row <= k-3 is written and every step <= k-4 of every group
+//            is complete: it may test the extrema of row k-4 (rows k-5..k-3) and overwrite ring slot k mod 8 (last
+//            read for rows k-9..k-7 in steps k-5, k-4 and -- by this same group -- k-3).
 // ================================================================================================
+#ifndef D3_EXP_NOEXT
+#define D3_EXP_NOEXT 0     // timing experiment only: no extrema tests (24.0 instead of 28.4 us per image)
+#endif
 #define D3_THREADS 512
 #define D3_PT 128
 #define D3_RS 8
@@ -430,6 +443,7 @@ __device__ __forceinline__ void nb_arrive(int id, int n) { asm volatile("bar.arr
 #define NB_EMPTY 4     // + group (3)
 #define NB_DONE 7      // + group (3)
 #define NB_PINT 10
+#define NB_LATE 11     // + group (3)
 
 struct D3Item {
   int level, img, x0, ry0, hs, w, h;
@@ -469,9 +483,25 @@ __device__ __noinline__ void d3_extrema(const D3Item &I, int j, int pt, const fl
     const int o = p * D2_RROWF + 2 * dc + hf;
     const float c = r0[o];
     if (!(fabsf(c) > I.thresh)) continue;
+    // the strict 26-neighbour test of cudaSiftD.cu:1340-1358 in two stages (the outcome is the same): the 8 neighbours
+    // in the candidate's own plane first -- most candidates fail there, and the other 18 values are never loaded
     float v[3][3][3];
+    bool mx = true, mn = true;
 #pragma unroll
-    for (int pp = 0; pp < 3; pp++)
+    for (int dx = 0; dx < 3; dx++) {
+      const int oo = o + 2 * (dx - 1);
+      v[1][0][dx] = rm[oo];
+      v[1][1][dx] = r0[oo];
+      v[1][2][dx] = rp[oo];
+    }
+#pragma unroll
+    for (int dy = 0; dy < 3; dy++)
+#pragma unroll
+      for (int dx = 0; dx < 3; dx++)
+        if (dy != 1 || dx != 1) { mx = mx && (c > v[1][dy][dx]); mn = mn && (c < v[1][dy][dx]); }
+    if (!(c > 0.0f ? mx : mn)) continue;
+#pragma unroll
+    for (int pp = 0; pp < 3; pp += 2)
 #pragma unroll
       for (int dx = 0; dx < 3; dx++) {
         const int oo = o + (pp - 1) * D2_RROWF + 2 * (dx - 1);
@@ -479,25 +509,18 @@ __device__ __noinline__ void d3_extrema(const D3Item &I, int j, int pt, const fl
         v[pp][1][dx] = r0[oo];
         v[pp][2][dx] = rp[oo];
       }
-    bool mx = true, mn = true;
 #pragma unroll
-    for (int pp = 0; pp < 3; pp++)
+    for (int pp = 0; pp < 3; pp += 2)
 #pragma unroll
       for (int dy = 0; dy < 3; dy++)
 #pragma unroll
-        for (int dx = 0; dx < 3; dx++)
-          if (pp != 1 || dy != 1 || dx != 1) { mx = mx && (c > v[pp][dy][dx]); mn = mn && (c < v[pp][dy][dx]); }
+        for (int dx = 0; dx < 3; dx++) { mx = mx && (c > v[pp][dy][dx]); mn = mn && (c < v[pp][dy][dx]); }
     if (c > 0.0f ? mx : mn) {
       const int gx = I.x0 + dc, gy = (hf ? I.ry0 + I.hs - 1 : I.ry0 - 1) + j;
       const unsigned int tag = (unsigned)gx | ((unsigned)gy << 13) | ((unsigned)(p - 1) << 26) | ((unsigned)I.level << 29);
       if (I.cells) {                                // extrema per 30x8 block and scale (reference cap, cudaSiftD.cu:1371)
         const int cell = I.cellBase + ((gy >> 3) * I.cellsX + gx / 30) * CS_NUM_SCALES + (p - 1);
-        unsigned int *cw = I.cells + (cell >> 2);
-        const unsigned old = atomicAdd(cw, 1u << (8 * (cell & 3)));
-        if (((old >> (8 * (cell & 3))) & 0xff) == (unsigned)I.capLimit) {      // the 33rd extremum of this cell
-          const unsigned at = atomicAdd(&I.counters[3], 1u);
-          if (at < CS_OVF_MAX) I.ovf[at] = (unsigned)cell;
-        }
+        atomicAdd(I.cells + (cell >> 2), 1u << (8 * (cell & 3)));     // RED (see detect2_kernel)
       }
       d2_refine(v, gx, gy, p - 1, I.subsampling, I.lowestScale, I.edgeLimit, I.factor, tag, s_kq, s_kn, I.pts,
                 &I.counters[0], I.maxPts);
@@ -635,9 +658,11 @@ detect3_kernel(const __grid_constant__ Detect2Params P)
       d3_vertical<(8 + (p)) % 9>(W0, W1, n0, n1, kv, s_v + ((p) % D3_NB) * D2_VBUF2 + pt);                    \
       n0 = x0n; n1 = x1n;                                                                                     \
     }                                                                                                         \
-    /* the group's previous step (m-3, with the extrema of row m-7) is complete */                            \
+    /* DONE: the group's previous step (m-3) has written its DoG row and candidate list.  LATE: step m-4 (another */ \
+    /* group) is complete including its extrema tests (rows m-9..m-7, list of row m-8) */                     \
     if (m >= D3_NB) nb_sync(NB_DONE + (p) % D3_NB, 2 * D3_PT);                                                \
-    if (pt == 0 && m >= 7) s_cnt[(m - 7) & (D3_RS - 1)] = 0;     /* list of row m-7: next used at step m+1 */   \
+    if (m >= D3_NB + 1) nb_sync(NB_LATE + ((p) + 2) % D3_NB, 2 * D3_PT);                                      \
+    if (pt == 0 && m >= 8) s_cnt[m & (D3_RS - 1)] = 0;           /* list of row m-8: used again by step m */    \
     nb_arrive(NB_FULL + (p) % D3_NB, 2 * D3_PT);               /* in the drain steps: only releases the tests */ \
     if (pt == 0 && m >= D3_NB && m < nsteps) {                                                                \
       /* past EMPTY of this step every producer has finished step m-1: refill the slots read up to then */     \
@@ -681,14 +706,20 @@ detect3_kernel(const __grid_constant__ Detect2Params P)
       const int tig = tid & 127;                                // thread index within the group
       for (int k = g; k < nsteps + 3; k += D3_NB) {
         const int q = k & (D3_RS - 1);
+        // LATE: this group's previous step (k-3) is complete, extrema tests included.  It is signalled here, after the
+        // group has passed FULL of step k, and not at the end of step k-3: the producers consume it at their step k+1,
+        // which is before they can signal FULL of step k+3, so two arrivals never pile up on the barrier.
+        const bool late = k >= D3_NB && k - D3_NB <= nsteps - 2;
         if (k >= nsteps) {                                      // drain: only the extrema of the last rows
           nb_sync(NB_FULL + g, 2 * D3_PT);
-          if (k - 4 <= hs) d3_extrema(I, k - 4, tig, s_ring, s_list, s_cnt, s_kq, &s_kn);
+          if (late) nb_arrive(NB_LATE + g, 2 * D3_PT);
+          if (k - 4 <= hs && s_cnt[(k - 4) & (D3_RS - 1)] != 0) d3_extrema(I, k - 4, tig, s_ring, s_list, s_cnt, s_kq, &s_kn);
           continue;
         }
         const bool rowsTested = testable && k >= 1 && k <= hs;
         const bool okA = ry0 - 1 + k <= h - 2, okB = ry0 + hs - 1 + k <= h - 2;
         nb_sync(NB_FULL + g, 2 * D3_PT);
+        if (late) nb_arrive(NB_LATE + g, 2 * D3_PT);
 #pragma unroll
         for (int pass = 0; pass < 2; pass++) {
           const int cg = 16 * pass + 4 * wg + cgl;
@@ -732,8 +763,16 @@ detect3_kernel(const __grid_constant__ Detect2Params P)
               const float2 a = upk(dg[d]);
               const int dc = 8 * cg + d;
               if (dc >= 1 && dc <= D2_TESTED && x0 + dc <= w - 2) colok |= 0x101u << d;
-              if (okA && fabsf(a.x) > thresh) bits |= 1u << d;
-              if (okB && fabsf(a.y) > thresh) bits |= 0x100u << d;
+              // a necessary condition that is already in registers: an extremum beats its left and right neighbours
+              // (columns 1..6 of the lane's 8; the two outer columns are decided by the full test)
+              bool ex = true, ey = true;
+              if (d >= 1 && d <= 6) {
+                const float2 l = upk(dg[d - 1]), r = upk(dg[d + 1]);
+                ex = a.x > 0.0f ? (a.x > l.x && a.x > r.x) : (a.x < l.x && a.x < r.x);
+                ey = a.y > 0.0f ? (a.y > l.y && a.y > r.y) : (a.y < l.y && a.y < r.y);
+              }
+              if (okA && ex && fabsf(a.x) > thresh) bits |= 1u << d;
+              if (okB && ey && fabsf(a.y) > thresh) bits |= 0x100u << d;
             }
             bits &= colok;
             if (bits) {
@@ -747,8 +786,9 @@ detect3_kernel(const __grid_constant__ Detect2Params P)
             }
           }
         }
-        if (k >= 5) d3_extrema(I, k - 4, tig, s_ring, s_list, s_cnt, s_kq, &s_kn);   // rows k-5..k-3 are complete
-        nb_arrive(NB_DONE + g, 2 * D3_PT);
+        nb_arrive(NB_DONE + g, 2 * D3_PT);                       // row k and its candidate list are written
+        // rows k-5..k-3 are complete; the call (out of line: registers) only when the row has candidates at all
+        if (!D3_EXP_NOEXT && k >= 5 && s_cnt[(k - 4) & (D3_RS - 1)] != 0) d3_extrema(I, k - 4, tig, s_ring, s_list, s_cnt, s_kq, &s_kn);
       }
     }
     __syncthreads();
@@ -762,6 +802,20 @@ detect3_kernel(const __grid_constant__ Detect2Params P)
   }
 }
 
+
+// once per device, outside any stream capture (Pipeline2::init)
+static int g_d2_table[64];
+int detect2_init_device()
+{
+  int dev = 0;
+  CS_CUDA(cudaGetDevice(&dev));
+  if (dev < 64 && g_d2_table[dev]) return 0;
+  d2_fill_pow_table<<<1, 32>>>();
+  CS_CUDA(cudaGetLastError());
+  CS_CUDA(cudaDeviceSynchronize());
+  if (dev < 64) g_d2_table[dev] = 1;
+  return 0;
+}
 
 static int g_d2_configured[64];
 int g_d2_variant = 2;     // tuning: 2 = warp-specialised detect3 (default); 0 / 1 = detect2 with 2 / 1 CTAs per SM
