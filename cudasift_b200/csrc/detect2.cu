@@ -456,7 +456,15 @@ struct D3Item {
 };
 
 // Extrema of step j (DoG rows ry0-1+j / ry0+hs-1+j) by the 128 producer threads; rows j-1, j, j+1 are complete.
-__device__ __noinline__ void d3_extrema(const D3Item &I, int j, int pt, const float *s_ring, const unsigned short *s_list,
+#ifndef D3_EXT_INLINE
+#define D3_EXT_INLINE 1    // inlined: 27.5 vs 27.9 us per image (0 = out of line)
+#endif
+#if D3_EXT_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+void d3_extrema(const D3Item &I, int j, int pt, const float *s_ring, const unsigned short *s_list,
                                         const int *s_cnt, D2Keypoint *s_kq, int *s_kn)
 {
   const int qj = j & (D3_RS - 1);
