@@ -40,10 +40,11 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 W, H, OCTAVES, INIT_BLUR, THRESH, MAX_PTS = 1920, 1080, 5, 1.0, 3.0, 32768
 REC = 576
 # packed FP32 instructions (FFMA2 + FADD2 + FMUL2, warp level) the detector executes per 1080p image, and the DRAM
-# traffic of the dominant kernels per image: ncu --set full captures under profiles/ (r02_prof_*.txt)
-DETECT_PACKED_WARP_INSTR = 6.22e6
-DETECT_DRAM_BYTES = 11.4e6
-PYR_DRAM_BYTES = 18.9e6
+# traffic of the dominant kernels per image: one ncu --set full capture of a batch of 16 (profiles/r02_prof_extract.txt,
+# profiles/r02_sass_hist_detect3.txt): (48.23 + 33.16 + 12.06) M / 16, (178.7 + 5.3) MB / 16, (152.3 + 116.9) MB / 16
+DETECT_PACKED_WARP_INSTR = 5.84e6
+DETECT_DRAM_BYTES = 11.5e6
+PYR_DRAM_BYTES = 16.8e6
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libcudasift_ref.so")
 
 
@@ -376,7 +377,7 @@ def bench_roofline(cs, ex, ptrs, pitch, b, value, world, pts_per_image):
     return {"bound": "hbm", "kernel": "detect3_kernel (8-scale blur + DoG + 3x3x3 extrema, all octaves, whole batch per launch)",
             "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
             "traffic": DETECT_DRAM_BYTES * b, "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full "
-            "capture of detect3_kernel (profiles/r02_prof_detect.txt), per launch of a batch of %d" % b,
+            "capture of detect3_kernel (profiles/r02_prof_extract.txt), per launch of a batch of %d" % b,
             "peak_source": how, "algorithmic_bytes_per_launch": detect_bytes * b, "units_per_launch": b,
             "avg_launch_ms": round(float(detect_ms * b), 4),
             "stage_ms": {"lowpass_scaledown": round(float(pa_ms), 4), "scaledown_chain": round(float(chain_ms), 4),
@@ -389,7 +390,7 @@ def bench_roofline(cs, ex, ptrs, pitch, b, value, world, pts_per_image):
             "pyramid": {"kernel": "pyr_lowpass_sd_kernel (LowPass + first ScaleDown, TMA-fed)", "bound": "hbm",
                         "algorithmic_bytes_per_image": pyr_bytes, "achieved": round(pyr_gbs, 1), "peak": peak,
                         "frac": round(pyr_gbs / peak, 4), "traffic": PYR_DRAM_BYTES * b,
-                        "traffic_source": "ncu capture, profiles/r02_prof_pyramid.txt"},
+                        "traffic_source": "ncu capture, profiles/r02_prof_extract.txt"},
             "pipeline_algorithmic_bytes": int(pipeline_bytes),
             "pipeline_frac_at_value": round(pipeline_bytes * value / world / 1e9 / peak, 4)}
 

@@ -730,6 +730,7 @@ int cs_set_tuning(const char *key, int value)
   if (key && strcmp(key, "d2_variant") == 0) { cs::g_d2_variant = value; return 0; }
   if (key && strcmp(key, "d2_hs") == 0) { cs::g_d2_hs = value; return 0; }
   if (key && strcmp(key, "pa_rows") == 0) { cs::g_pa_rows = value; return 0; }
+  if (key && strcmp(key, "sd_split") == 0) { cs::g_sd_split = value; return 0; }
   if (key && strcmp(key, "cap32") == 0) { cs::g_cap32 = value ? 1 : 0; return 0; }
   if (key && strcmp(key, "cap32_limit") == 0) { cs::g_cap_limit = (value > 0 && value < 200) ? value : 32; return 0; }
   cs::set_error("cs_set_tuning: unknown key");

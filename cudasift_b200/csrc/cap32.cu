@@ -40,15 +40,24 @@ cap32_fixup_kernel(const __grid_constant__ Detect2Params P)
   {
     const unsigned int *cells = P.cells + (size_t)img * P.cellWords;
     const unsigned lim = (unsigned)P.capLimit;
-    for (int i = tid; i < P.cellWords; i += C32_THREADS) {
-      const unsigned v = __ldg(cells + i);
-      if (v == 0) continue;
+    // 16 independent loads per thread and round trip: the scan is one CTA per image, so it is pure latency
+    for (int i0 = tid; i0 < P.cellWords; i0 += 16 * C32_THREADS) {
+      unsigned v[16];
 #pragma unroll
-      for (int b = 0; b < 4; b++)
-        if (((v >> (8 * b)) & 0xff) > lim) {
-          const int at = atomicAdd(&s_novf, 1);
-          if (at < CS_OVF_MAX) s_ovf[at] = (unsigned)(4 * i + b);
-        }
+      for (int u = 0; u < 16; u++) {
+        const int i = i0 + u * C32_THREADS;
+        v[u] = i < P.cellWords ? __ldg(cells + i) : 0u;
+      }
+#pragma unroll
+      for (int u = 0; u < 16; u++) {
+        if (v[u] == 0) continue;
+#pragma unroll
+        for (int b = 0; b < 4; b++)
+          if (((v[u] >> (8 * b)) & 0xff) > lim) {
+            const int at = atomicAdd(&s_novf, 1);
+            if (at < CS_OVF_MAX) s_ovf[at] = (unsigned)(4 * (i0 + u * C32_THREADS) + b);
+          }
+      }
     }
   }
   __syncthreads();

@@ -65,7 +65,7 @@ struct LaplaceTaps {
 int launch_lowpass(const float *src, int srcPitch, float *dst, int dstPitch, int w, int h,
                    const Taps9 &taps, cudaStream_t st);
 int launch_scaledown(const float *src, float *dst, int w, int h, int pitch, int newpitch,
-                     const Taps5 &taps, cudaStream_t st);
+                     const Taps5 &taps, cudaStream_t st, int batch = 1, long long srcStride = 0, long long dstStride = 0);
 int launch_scaleup(const float *src, float *dst, int w, int h, int pitch, int newpitch,
                    cudaStream_t st);
 int launch_u8_to_float(const uint8_t *src, int srcPitch, float *dst, int dstPitch, int w, int h, cudaStream_t st);

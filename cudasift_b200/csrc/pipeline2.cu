@@ -65,6 +65,7 @@ int g_d2_hs = 0;          // rows per detector stream (0 = choose by batch size)
 int g_pa_rows = 0;        // level-0 rows per CTA of kernel A (0 = choose by batch size)
 int g_cap32 = -1;         // reference cap of 32 extrema per 30x8 block and scale: 1 on (default), 0 off
 int g_cap_limit = 32;     // tests only
+int g_sd_split = 1;       // batches: level 1 -> 2 by the tiled ScaleDown kernel, the chain kernel for the small levels (0 = chain only)
 
 static bool cap32_enabled()
 {
@@ -274,7 +275,16 @@ int Pipeline2::enqueue(int n, const float *const *d_imgs, int pitch, double init
   if ((r = launch_pyr_a(pa, n, st)) < 0) return r;
   if ((r = debug_stage(st, "pyr_lowpass_sd")) < 0) return r;
   if (ev) cudaEventRecord(ev[1], st);
-  for (int from = 1; from + 1 < numLevels; from += 3) {                     // cudaSiftH.cu:153-157, three levels per launch
+  int from0 = 1;
+  if (g_sd_split && n >= 2 && numLevels >= 4) {
+    // a whole batch keeps the 64x16-tile ScaleDown of round 1 busy (13 % halo); the chain kernel's 8x8 tiles recompute
+    // 1.6x on the level it would produce first, which is the large one.  It keeps the small levels.
+    if ((r = launch_scaledown(arena + levOff[1], arena + levOff[2], lw[1], lh[1], lp[1], lp[2], sdTaps, st, n,
+                              (long long)perImage, (long long)perImage)) < 0) return r;
+    if ((r = debug_stage(st, "scaledown 1->2")) < 0) return r;
+    from0 = 2;
+  }
+  for (int from = from0; from + 1 < numLevels; from += 3) {                 // cudaSiftH.cu:153-157, three levels per launch
     PyrBParams pb;
     memset(&pb, 0, sizeof(pb));
     pb.steps = numLevels - 1 - from < 3 ? numLevels - 1 - from : 3;

@@ -150,8 +150,10 @@ int launch_lowpass(const float *src, int srcPitch, float *dst, int dstPitch, int
 
 __global__ void __launch_bounds__(256)
 scaledown_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, int h, int pitch,
-                 int newpitch, const __grid_constant__ Taps5 taps)
+                 int newpitch, const __grid_constant__ Taps5 taps, long long srcStride, long long dstStride)
 {
+  src += (size_t)blockIdx.z * srcStride;      // batched launch: image blockIdx.z
+  dst += (size_t)blockIdx.z * dstStride;
   __shared__ __align__(16) float s_in[SD_IH][SD_IW];
   __shared__ __align__(16) float s_h[SD_IH][SD_W];
   const int tid = threadIdx.x;
@@ -206,11 +208,11 @@ scaledown_kernel(const float *__restrict__ src, float *__restrict__ dst, int w, 
 }
 
 int launch_scaledown(const float *src, float *dst, int w, int h, int pitch, int newpitch,
-                     const Taps5 &taps, cudaStream_t st)
+                     const Taps5 &taps, cudaStream_t st, int batch, long long srcStride, long long dstStride)
 {
   if (w / 2 < 1 || h / 2 < 1) return 0;
-  dim3 grid(idivup(w / 2, SD_W), idivup(h / 2, SD_H));
-  scaledown_kernel<<<grid, 256, 0, st>>>(src, dst, w, h, pitch, newpitch, taps);
+  dim3 grid(idivup(w / 2, SD_W), idivup(h / 2, SD_H), batch);
+  scaledown_kernel<<<grid, 256, 0, st>>>(src, dst, w, h, pitch, newpitch, taps, srcStride, dstStride);
   count_launch();
   CS_CUDA(cudaGetLastError());
   return 0;
