@@ -244,7 +244,7 @@ int Pipeline2::fill_pyr_a(PyrAParams &pa, int n, const float *const *d_imgs, int
   float sigma = (float)(initBlur > (double)0.001f ? initBlur : (double)0.001f);   // cudaSiftH.cu:112
   lowpass_taps(sigma, pa.lp.k);
   pa.sd = sdTaps;
-  int rows = g_pa_rows > 0 ? g_pa_rows : (n >= 8 ? 64 : (n >= 2 ? 48 : 32));   // rows per warp (+12 halo rows each); measured: 64 beats 120 at batch 16-32
+  int rows = g_pa_rows > 0 ? g_pa_rows : (n >= 8 ? 72 : (n >= 2 ? 48 : 32));   // rows per warp (+12 halo rows each); measured at batch 16 / 32: 64: 6.5 / 5.7 us, 72: 6.0 / 5.5, 90: 6.8 / 5.5, 108: 7.3 / 5.8
   rows = (rows + 1) & ~1;
   pa.rowsPerCta = rows;
   pa.stripsX = idivup(lw[0], CS_PA_OWN);

@@ -15,7 +15,7 @@ keys = sys.argv[1:] or ["d2_variant=0", "d2_variant=1"]
 for spec in keys:
     for kv in spec.split(","):
         k, v = kv.split("="); cs.set_tuning(k, int(v))
-    for B in (1, 32):
+    for B in [int(x) for x in os.environ.get("R2_BATCHES", "1,32").split(",")]:
         ex = cs.Extractor(w, h, 5, 32768, False, batch=B)
         t = []
         for i in range(8):
