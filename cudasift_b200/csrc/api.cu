@@ -426,13 +426,17 @@ static int match_sync(SiftPoint *d_s1, int n1, SiftPoint *d_s2, int n2, SiftPoin
     r = match_exact(d_s1, n1, d_s2, n2, c->stream);
     c->matchStats[0] = c->matchStats[1] = c->matchStats[2] = 0; c->matchStats[3] = 1;
   }
-  if (r < 0) return r;
-  if (h_s1) {                                                              // matching.cu:1195-1199
-    CS_CUDA(cudaMemcpy2DAsync(&h_s1[0].score, sizeof(SiftPoint), &d_s1[0].score, sizeof(SiftPoint),
-                              5 * sizeof(float), n1, cudaMemcpyDeviceToHost, c->stream));
+  if (r >= 0 && h_s1) {                                                    // matching.cu:1195-1199
+    cudaError_t ce = cudaMemcpy2DAsync(&h_s1[0].score, sizeof(SiftPoint), &d_s1[0].score, sizeof(SiftPoint),
+                                       5 * sizeof(float), n1, cudaMemcpyDeviceToHost, c->stream);
+    if (ce != cudaSuccess) { set_error("MatchSiftData: result copy failed: %s", cudaGetErrorString(ce)); r = CS_E_CUDA; }
   }
-  cudaEventRecord(e1, c->stream);
-  CS_CUDA(cudaStreamSynchronize(c->stream));
+  if (r >= 0) {
+    cudaEventRecord(e1, c->stream);
+    cudaError_t ce = cudaStreamSynchronize(c->stream);
+    if (ce != cudaSuccess) { set_error("MatchSiftData: %s", cudaGetErrorString(ce)); r = CS_E_CUDA; }
+  }
+  if (r < 0) { cudaEventDestroy(e0); cudaEventDestroy(e1); return r; }     // no event leak on the error paths
   float t = 0; cudaEventElapsedTime(&t, e0, e1);
   cudaEventDestroy(e0); cudaEventDestroy(e1);
   if (useTensor) match_tensor_stats(c->matchStats);

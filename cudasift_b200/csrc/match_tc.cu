@@ -539,7 +539,12 @@ t3_resolve_kernel(const TcPlan pl, const T3Buffers bf, SiftPoint *__restrict__ s
   const bool use2 = rel && I2 >= 0 && S >= low;
   const unsigned int certMask = (__ballot_sync(FULL, cert) >> (8 * sub)) & 0xffu;
   const bool ok = valid && rowOk && certMask == 0xffu;
-  if (valid && !ok && p == 0) bf.fbRows[atomicAdd(&bf.counters[0], 1u)] = row;
+  if (valid && !ok && p == 0) {
+    // every row lists itself at most once, so the index stays below n1 when the counter started at zero; the clamp
+    // keeps a stale counter (a previous call that failed half-way) from writing past the list
+    const unsigned at = atomicAdd(&bf.counters[0], 1u);
+    if (at < (unsigned)pl.n_mt * T3_MT) bf.fbRows[at] = row;
+  }
   // candidate group list (first groups, then second groups)
   const unsigned int b1 = (__ballot_sync(FULL, ok && use1) >> (8 * sub)) & 0xffu;
   const unsigned int b2 = (__ballot_sync(FULL, ok && use2) >> (8 * sub)) & 0xffu;
@@ -652,12 +657,16 @@ bool match_tensor_supported()
   return major == 10;
 }
 
+// One workspace per device, used on the caller's stream: like the reference (function-local static caches,
+// cudaSiftH.cu:310,409) the matcher is single-threaded per device -- two host threads matching on the same device at
+// the same time would share the tables and the flag areas.
 struct T3Workspace {
   T3Buffers bf = {};
   size_t cap[8] = {};
   unsigned int *h_counters = nullptr;
   float *flags = nullptr;         // 2 x 16 words: [0] max norm of set 2, [1] bad-input flag, [4..7] counters
   unsigned long long calls = 0;
+  bool dirty = false;             // a call returned with an error after it had started to use the current flag area
   bool configured = false;
   bool pendingStats = false;
 };
@@ -702,7 +711,8 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
   }
   bf.bmax = ws.flags + 16 * (ws.calls & 1);
   float *nextFlags = ws.flags + 16 * ((ws.calls + 1) & 1);
-  ws.calls++;
+  if (ws.dirty) CS_CUDA(cudaMemsetAsync(ws.flags, 0, 128, st));     // a previous call failed between its launches
+  ws.dirty = true;                                                  // until this call's launches are all in
   bf.counters = reinterpret_cast<unsigned int *>(bf.bmax) + 4;
   if (!ws.configured) {
     CS_CUDA(cudaFuncSetAttribute(t3_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_BYTES));
@@ -739,6 +749,8 @@ int match_tensor(SiftPoint *s1, int n1, const SiftPoint *s2, int n2, cudaStream_
             ms[0] * 1e3f, ms[1] * 1e3f, ms[2] * 1e3f, ms[3] * 1e3f, ms[4] * 1e3f);
   }
   CS_CUDA(cudaMemcpyAsync(ws.h_counters, bf.bmax, 64, cudaMemcpyDeviceToHost, st));
+  ws.calls++;                           // the prep kernel of this call cleared the other flag area for the next one
+  ws.dirty = false;
   ws.pendingStats = true;               // read by match_tensor_stats() after the caller's synchronize
   return 0;
 }
