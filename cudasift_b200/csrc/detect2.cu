@@ -425,8 +425,14 @@ detect2_kernel(const __grid_constant__ Detect2Params P)
 //            is complete: it may test the extrema of row k-4 (rows k-5..k-3) and overwrite ring slot k mod 8 (last
 //            read for rows k-9..k-7 in steps k-5, k-4 and -- by this same group -- k-3).
 // ================================================================================================
+// timing experiments (phase attribution, scripts/expbuild.sh -DD3_EXP=mask; results are wrong when set):
+// 1 no extrema tests, 2 no threshold flags / candidate lists, 4 no DoG ring stores, 8 no horizontal arithmetic and
+// shuffles (the loads stay), 16 no vertical arithmetic in the producers
+#ifndef D3_EXP
+#define D3_EXP 0
+#endif
 #ifndef D3_EXP_NOEXT
-#define D3_EXP_NOEXT 0     // timing experiment only: no extrema tests (24.0 instead of 28.4 us per image)
+#define D3_EXP_NOEXT (D3_EXP & 1)     // timing experiment only: no extrema tests (24.0 instead of 28.4 us per image)
 #endif
 #define D3_THREADS 512
 #define D3_PT 128
@@ -544,6 +550,11 @@ __device__ __forceinline__ void d3_vertical(f32x2 (&W0)[9], f32x2 (&W1)[9], f32x
 #define D3_WI(i) ((PH + 1 + (i)) % 9)
   W0[PH] = n0;
   W1[PH] = n1;
+  if (D3_EXP & 16) {
+#pragma unroll
+    for (int s = 0; s < CS_LAPLACE_S; s++) { vdst[s * D2_VROW2] = upk(W0[D3_WI(4)]); vdst[s * D2_VROW2 + 128] = upk(W1[D3_WI(4)]); }
+    return;
+  }
   {
     const f32x2 c = W0[D3_WI(4)];
     const f32x2 p1 = add2(W0[D3_WI(3)], W0[D3_WI(5)]), p2 = add2(W0[D3_WI(2)], W0[D3_WI(6)]);
@@ -744,13 +755,14 @@ detect3_kernel(const __grid_constant__ Detect2Params P)
           f32x2 dg[8];
 #pragma unroll
           for (int d = 0; d < 8; d++) {
+            if (D3_EXP & 8) { dg[d] = add2(V[d + 4], V[d + 8]); continue; }
             const f32x2 o = d2_sym9(kh, V[d + 4], add2(V[d + 3], V[d + 5]), add2(V[d + 2], V[d + 6]),
                                     add2(V[d + 1], V[d + 7]), add2(V[d], V[d + 8]));
             const float2 of = upk(o);
             const float plo = __shfl_up_sync(0xffffffffu, of.x, 1), phi = __shfl_up_sync(0xffffffffu, of.y, 1);
             dg[d] = sub2(o, pk2(plo, phi));                 // blur[s] - blur[s-1]: DoG plane s-1 (cudaSiftD.cu:1790)
           }
-          if (act && hs_ >= 1) {
+          if (!(D3_EXP & 4) && act && hs_ >= 1) {
             float4 *dst = reinterpret_cast<float4 *>(rdst0 + q * D2_RSLOTF + 256 * pass);
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -764,7 +776,7 @@ detect3_kernel(const __grid_constant__ Detect2Params P)
             const float2 a = upk(dg[d]);
             m = fmaxf(m, fmaxf(fabsf(a.x), fabsf(a.y)));
           }
-          if (m > thresh && rowsTested && act) {
+          if (!(D3_EXP & 2) && m > thresh && rowsTested && act) {
             unsigned bits = 0, colok = 0;
 #pragma unroll
             for (int d = 0; d < 8; d++) {
