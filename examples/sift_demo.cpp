@@ -6,6 +6,7 @@
 //
 //   sift_demo left.{pgm,png} right.{pgm,png} [--thresh T] [--octaves N] [--repeat R] [--device D]
 //             [--ransac LOOPS] [--out marked.pgm] [--style marks|reference] [--print K]
+//   sift_demo --decode-only in.{pgm,png} out.pgm          (image decoding only, no GPU needed)
 //
 // --style reference draws what the reference's PrintMatchData draws (mainSift.cpp:150-200): a line to the matched
 // feature for matches within 5 px of the homography, and a black-and-white cross of half-length 1.41*scale per feature.
@@ -221,6 +222,12 @@ double now_ms()
 
 int main(int argc, char **argv)
 {
+  if (argc == 4 && !strcmp(argv[1], "--decode-only")) {        // image I/O check without a GPU: in.{png,pgm} -> out.pgm
+    GrayImage img;
+    if (!read_image(argv[2], &img) || !write_pgm(argv[3], img)) return 1;
+    printf("Image size = (%d,%d)\n", img.w, img.h);
+    return 0;
+  }
   if (argc < 3) {
     fprintf(stderr, "usage: %s left.{pgm,png} right.{pgm,png} [--thresh T] [--octaves N] [--repeat R] [--device D] "
                     "[--ransac LOOPS] [--out marked.pgm] [--style marks|reference] [--print K]\n", argv[0]);

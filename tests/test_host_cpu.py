@@ -88,3 +88,31 @@ def test_new_abi_symbols_present():
         assert hasattr(L, name), name
     assert L.cs_max_batch() == 32
     assert L.cs_set_tuning(b"cap32_limit", 32) == 0 and L.cs_set_tuning(b"legacy", 0) == 0
+
+
+def test_demo_png_decoder_matches_opencv(tmp_path):
+    """examples/sift_demo.cpp decodes PNG itself (zlib inflate + the five PNG filters) and converts colour to grey with
+    cv::cvtColor's fixed-point weights: checked here without a GPU (--decode-only) on grey, RGB and RGBA files written by
+    OpenCV, whose encoder chooses among the filter types per row."""
+    import subprocess
+    cv2 = pytest.importorskip("cv2")
+    from cudasift_b200 import build
+    from cudasift_b200.synth import synth_image
+    demo = build.build_demo()
+    assert demo and os.path.exists(demo)
+    rng = np.random.default_rng(5)
+    base = np.clip(synth_image(333, 217, seed=3), 0, 255).astype(np.uint8)
+    rgb = np.stack([base, np.roll(base, 5, 1), (rng.random(base.shape) * 255).astype(np.uint8)], axis=2)
+    rgba = np.concatenate([rgb, np.full(base.shape + (1,), 200, np.uint8)], axis=2)
+    for name, img, want in (("grey", base, base), ("rgb", rgb, cv2.cvtColor(rgb, cv2.COLOR_BGR2GRAY)),
+                            ("rgba", rgba, cv2.cvtColor(rgb, cv2.COLOR_BGR2GRAY))):
+        src, dst = str(tmp_path / (name + ".png")), str(tmp_path / (name + ".pgm"))
+        assert cv2.imwrite(src, img)
+        r = subprocess.run([demo, "--decode-only", src, dst], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=60)
+        assert r.returncode == 0, r.stdout
+        with open(dst, "rb") as f:
+            assert f.readline() == b"P5\n"
+            w, h = [int(v) for v in f.readline().split()]
+            assert f.readline() == b"255\n"
+            got = np.frombuffer(f.read(), np.uint8).reshape(h, w)
+        assert np.array_equal(got, want), name
