@@ -244,7 +244,7 @@ int Pipeline2::fill_pyr_a(PyrAParams &pa, int n, const float *const *d_imgs, int
   float sigma = (float)(initBlur > (double)0.001f ? initBlur : (double)0.001f);   // cudaSiftH.cu:112
   lowpass_taps(sigma, pa.lp.k);
   pa.sd = sdTaps;
-  int rows = g_pa_rows > 0 ? g_pa_rows : (n >= 8 ? 72 : (n >= 2 ? 48 : 32));   // rows per warp (+12 halo rows each); measured at batch 16 / 32: 64: 6.5 / 5.7 us, 72: 6.0 / 5.5, 90: 6.8 / 5.5, 108: 7.3 / 5.8
+  int rows = g_pa_rows > 0 ? g_pa_rows : (n >= 8 ? 72 : (n >= 2 ? 48 : 16));   // rows per warp (+12 halo rows each); measured at batch 16 / 32: 64: 6.5 / 5.7 us, 72: 6.0 / 5.5, 90: 6.8 / 5.5, 108: 7.3 / 5.8
   rows = (rows + 1) & ~1;
   pa.rowsPerCta = rows;
   pa.stripsX = idivup(lw[0], CS_PA_OWN);
@@ -312,7 +312,7 @@ int Pipeline2::enqueue(int n, const float *const *d_imgs, int pitch, double init
     dp.lev0Img[i] = arena + levOff[i]; dp.levPitch[i] = lp[i];
   }
   dp.imgStride = (long long)perImage;
-  const int hs = g_d2_hs > 0 ? g_d2_hs : (n >= 8 ? 96 : (n >= 2 ? 32 : 16));   // rows per stream (measured: 96 beats 64 by 0.3-0.5 us per image at batch 16-32)
+  const int hs = g_d2_hs > 0 ? g_d2_hs : (n >= 8 ? 96 : (n >= 2 ? 32 : 12));   // rows per stream (measured: 96 beats 64 by 0.3-0.5 us per image at batch 16-32)
   if ((r = get_items(n, hs, &dp.items, &dp.numItems)) < 0) return r;
   dp.maps = d_maps;
   dp.thresh = thresh; dp.edgeLimit = 10.0f; dp.factor = 1.0f / CS_NUM_SCALES;   // cudaSiftH.cu:213
