@@ -746,7 +746,7 @@ int cs_extract_launches_per_image(int numOctaves, int scaleUp)
   if (legacy_mode())   // lowpass + (numOctaves-1) scaledown + detect + describe (+ scaleup + rescale)
     return 1 + (numOctaves - 1) + 1 + 1 + (scaleUp ? 2 : 0);
   // level-0/1 kernel + ScaleDown chain (3 levels per launch) + detect + cap fix-up + describe (+ scaleup + rescale);
-  // a batch of n images costs the same number of launches
+  // a batch of n >= 2 images costs one launch more for the whole batch (level 1 -> 2 by the tiled ScaleDown kernel)
   return 1 + (numOctaves > 2 ? (numOctaves - 2 + 2) / 3 : 0) + 1 + (cs::g_cap32 == 0 ? 0 : 1) + 1 + (scaleUp ? 2 : 0);
 }
 

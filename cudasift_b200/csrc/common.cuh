@@ -122,7 +122,7 @@ int launch_dog_planes(const float *base, float *dog, int w, int h, int pitch,
 
 // ---- marching detector (detect2.cu): all octaves of a batch of images in one launch -----------
 #define CS_CNT_STRIDE 4       // per image: [0] primaries found, [1] total incl. secondaries, [2] spare, [3] overflowed cap cells
-#define CS_OVF_MAX 256        // overflowed (30x8 block, scale) cells recorded per image
+#define CS_OVF_MAX 256        // overflowed (30x8 block, scale) cells the fix-up kernel handles per image
 struct LaplaceTaps1 { float k[CS_LAPLACE_S][5]; };   // [scale][tap], tap 0 = centre
 struct D2Level {
   int w, h;
@@ -143,7 +143,6 @@ struct Detect2Params {
   int maxPts;
   // reference cap of 32 extrema per 30x8 block and scale (cudaSiftD.cu:1371,1379); cells == NULL: no cap
   unsigned int *cells;        // packed 8-bit counters, image i: cells + i * cellWords
-  unsigned int *ovf;          // image i: ovf + i * CS_OVF_MAX
   int cellWords;
   int capLimit;               // 32 (MEMWID, cudaSiftD.cu:1293); tests lower it to make the cap reachable
   int cellBase[CS_MAX_LEVELS], cellsX[CS_MAX_LEVELS];

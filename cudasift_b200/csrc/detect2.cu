@@ -457,7 +457,7 @@ struct D3Item {
   SiftPoint *pts;
   unsigned int *counters;
   int maxPts;
-  unsigned int *cells, *ovf;
+  unsigned int *cells;
   int cellBase, cellsX, capLimit;
 };
 
@@ -719,7 +719,6 @@ detect3_kernel(const __grid_constant__ Detect2Params P)
       I.counters = P.counters + (size_t)img * CS_CNT_STRIDE;
       I.maxPts = P.maxPts;
       I.cells = P.cells ? P.cells + (size_t)img * P.cellWords : nullptr;
-      I.ovf = P.ovf ? P.ovf + (size_t)img * CS_OVF_MAX : nullptr;
       I.cellBase = P.cellBase[level]; I.cellsX = P.cellsX[level]; I.capLimit = P.capLimit;
       const bool testable = hs_ >= 2 && hs_ <= 6;               // DoG planes 1..5
       const int tig = tid & 127;                                // thread index within the group

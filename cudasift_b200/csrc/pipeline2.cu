@@ -148,14 +148,14 @@ int Pipeline2::init(int w, int h, int octaves, bool up, int maxBatch, float *are
   CS_CUDA(cudaMalloc((void **)&d_maps, maps.size() * sizeof(CUtensorMap)));
   CS_CUDA(cudaMemcpy(d_maps, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
 
-  // per-launch state, cleared by one memset: [B x 4 counters][scheduler, 4 words][B x cellWords][B x CS_OVF_MAX]
+  // per-launch state, cleared by one memset: [B x 4 counters][scheduler, 4 words][B x cellWords]
   cellWords = 0;
   for (int i = 0; i < numLevels; i++) {
     cellsX[i] = idivup(lw[i], 30);
     cellBase[i] = cellWords * 4;
     cellWords += idivup(cellsX[i] * idivup(lh[i], 8) * CS_NUM_SCALES, 4);
   }
-  stateWords = (size_t)B * CS_CNT_STRIDE + 4 + (size_t)B * cellWords + (size_t)B * CS_OVF_MAX;
+  stateWords = (size_t)B * CS_CNT_STRIDE + 4 + (size_t)B * cellWords;
   CS_CUDA(cudaMalloc((void **)&d_state, stateWords * sizeof(unsigned int)));
 
   memset(lapTaps, 0, sizeof(lapTaps));
@@ -261,7 +261,7 @@ int Pipeline2::enqueue(int n, const float *const *d_imgs, int pitch, double init
   CS_CUDA(cudaMemsetAsync(d_state, 0, stateWords * sizeof(unsigned int), st));   // cudaSiftH.cu:77
   if (ev) cudaEventRecord(ev[0], st);
   unsigned int *d_counters = d_state, *d_sched = d_state + (size_t)B * CS_CNT_STRIDE;
-  unsigned int *d_cells = d_sched + 4, *d_ovf = d_cells + (size_t)B * cellWords;
+  unsigned int *d_cells = d_sched + 4;
 
   if (scaleUp) {                                                            // cudaSiftH.cu:119-123
     for (int b = 0; b < n; b++)
@@ -317,7 +317,7 @@ int Pipeline2::enqueue(int n, const float *const *d_imgs, int pitch, double init
   dp.maps = d_maps;
   dp.thresh = thresh; dp.edgeLimit = 10.0f; dp.factor = 1.0f / CS_NUM_SCALES;   // cudaSiftH.cu:213
   dp.pts = d_pts; dp.ptsStride = ptsStride; dp.counters = d_counters; dp.sched = d_sched; dp.maxPts = maxPts;
-  if (cap32_enabled()) { dp.cells = d_cells; dp.ovf = d_ovf; dp.cellWords = cellWords; }
+  if (cap32_enabled()) { dp.cells = d_cells; dp.cellWords = cellWords; }
   dp.capLimit = g_cap_limit;
   if ((r = launch_detect2(dp, sms, st)) < 0) return r;
   if ((r = debug_stage(st, "detect2")) < 0) return r;

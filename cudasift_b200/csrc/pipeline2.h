@@ -19,7 +19,7 @@ struct Pipeline2 {
   cudaTextureObject_t *d_tex = nullptr;      // [image slot * CS_MAX_LEVELS + level]
   CUtensorMap *d_maps = nullptr;             // same indexing, box 256 x 1
   std::vector<CUtensorMap> upMaps;           // up-scaled inputs (scaleUp)
-  unsigned int *d_state = nullptr;           // counters | scheduler | cap cells | overflow lists (one memset)
+  unsigned int *d_state = nullptr;           // counters | scheduler | cap cells (one memset)
   size_t stateWords = 0;
   int cellWords = 0, cellBase[CS_MAX_LEVELS] = {}, cellsX[CS_MAX_LEVELS] = {};
   float lapTaps[8 * 12 * 16];
