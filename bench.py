@@ -5,8 +5,10 @@
   python bench.py --impl reference --gpus N ...            # the unmodified reference build
   (N>1: launched by `python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N`)
 
-A "step" is one pass of ExtractSift over a batch of synthetic 1920x1080 float images that are resident in HBM
-(32 distinct device buffers = 265 MB > the 126 MB L2, so every step re-reads its inputs from DRAM).
+A "step" is `rounds` passes of ExtractSift over a batch of synthetic 1920x1080 float images that are resident in HBM
+(32 distinct device buffers = 265 MB > the 126 MB L2, so every pass re-reads its inputs from DRAM).  `rounds` is chosen
+by the same rule in both arms so that the K timed steps cover >= 7680 images per GPU: the timed region then lasts
+>= 0.3 s and the in-process NVML sampler sees it (--steps 20 -> 12 rounds = 384 images per step; --steps 300 -> 1).
 Product arm:
   value    images/s, device-resident inputs, through the BATCHED extractor API (one launch per stage for a whole
            batch; every image has its own record slot, counts come back to the host every step)
@@ -67,11 +69,23 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", {}
 
 
-def workload_config(batch, distinct, pitch, features):
+MIN_TIMED_IMAGES = 7680   # per GPU: the timed region lasts >= 0.3 s at 24k images/s, so that clocks can be sampled in it
+
+
+def rounds_per_step(args):
+    """A step = `rounds` passes over the `batch` device-resident images.  Chosen by the same rule in both arms so that
+    K steps cover at least MIN_TIMED_IMAGES images per GPU (the driver runs --steps 20: 12 rounds of 32 images)."""
+    if args.rounds > 0:
+        return args.rounds
+    return max(1, -(-MIN_TIMED_IMAGES // (max(1, args.steps) * args.batch)))
+
+
+def workload_config(batch, distinct, pitch, features, rounds=1):
     """The `config` object: identical in both arms (same inputs, same parameters, same statistic)."""
     return {"workload": "ExtractSift 1920x1080 float, 5 octaves, initBlur 1.0, thresh 3.0 (BASELINE config #2)",
-            "images_per_step_per_gpu": batch, "distinct_images": distinct,
-            "l2_policy": "inputs larger than L2 (%d device images = %.0f MB per GPU)" % (batch, batch * pitch * H * 4 / 1e6),
+            "images_per_step_per_gpu": batch * rounds, "distinct_images": distinct,
+            "l2_policy": "inputs larger than L2 (%d device images = %.0f MB per GPU, %d pass(es) over them per step)"
+                         % (batch, batch * pitch * H * 4 / 1e6, rounds),
             "features_per_image": round(float(features), 1),
             "parallelism": "images sharded one process per GPU, no collective"}
 
@@ -235,9 +249,12 @@ def run_product(args):
     ev0 = [L.cs_event_create() for _ in range(S)]
     ev1 = [L.cs_event_create() for _ in range(S)]
 
+    R = rounds_per_step(args)
+
     def step_device():
-        for s in range(S):
-            exs[s].submit_device_batch(ptrs[s * b:(s + 1) * b], pitch, INIT_BLUR, THRESH, 0.0)
+        for _ in range(R):
+            for s in range(S):
+                exs[s].submit_device_batch(ptrs[s * b:(s + 1) * b], pitch, INIT_BLUR, THRESH, 0.0)
 
     for _ in range(args.warmup):
         step_device()
@@ -264,7 +281,7 @@ def run_product(args):
     clocks = sampler.stop()
     dev_ms = reduce_max(dist, dev_ms)
     wall = reduce_max(dist, wall)
-    n_images = args.steps * B * world
+    n_images = args.steps * B * R * world
     value = n_images / (dev_ms / 1e3)
     pts_per_image = float(np.mean(counts))            # all B images of the last step
 
@@ -275,7 +292,7 @@ def run_product(args):
             hp = L.cs_extractor_host_image_at(exs[s].handle, i)
             ctypes.memmove(hp, imgs[(s * b + i) % len(imgs)].ctypes.data, W * H * 4)
             hptrs.append(hp)
-    e2e_rounds = max(2, min(args.steps, 200) // 25)   # batches per extractor
+    e2e_rounds = max(16, min(args.steps, 200) // 12)  # batches per extractor: >= 512 images (~80 ms at the PCIe rate)
 
     def run_e2e(rounds):
         d2h = 0
@@ -306,12 +323,12 @@ def run_product(args):
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(B, len(imgs), pitch, pts_per_image),
+        "config": workload_config(B, len(imgs), pitch, pts_per_image, R),
         "api": "cs_extractor_submit_device_batch: %d extractor(s) x batch %d, one launch per stage per batch, CUDA graph, "
                "own record slot per image, counts read back every step" % (S, b),
         "clocks": clocks, "numa": numa,
-        "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": B * W * H * 4,
-                "d2h_bytes_per_step": int(d2h_bytes / e2e_images * B), "images": e2e_images * world,
+        "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": B * R * W * H * 4,
+                "d2h_bytes_per_step": int(d2h_bytes / e2e_images * B * R), "images": e2e_images * world,
                 "h2d_gbs_per_rank": round(h2d_gbs, 1),
                 "api": "cs_extractor_submit_host_batch / cs_extractor_wait_batch (pinned host buffers, %d batches of %d in flight)" % (S, b)},
         "gpu_launches": int(launches * world),
@@ -595,7 +612,7 @@ def run_reference(args):
             print(json.dumps({"impl": "reference", "metric": "1920x1080 images/sec ExtractSift", "value": cb["value"],
                               "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                               "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
-                              "config": workload_config(args.batch, len(imgs), pitch, 0),
+                              "config": workload_config(args.batch, len(imgs), pitch, 0, rounds_per_step(args)),
                               "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "images/s",
                                                           "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
         return
@@ -639,12 +656,15 @@ def run_reference(args):
     tmp = alloc(W, H, OCTAVES, False)
     counts = [0] * B
 
+    R = rounds_per_step(args)
+
     def step(download):
-        for i in range(B):
-            if download:
-                imgdown(c.byref(images[i]))
-            extract(c.byref(sd), c.byref(images[i]), OCTAVES, INIT_BLUR, THRESH, 0.0, False, tmp)
-            counts[i] = sd.numPts
+        for _ in range(R):
+            for i in range(B):
+                if download:
+                    imgdown(c.byref(images[i]))
+                extract(c.byref(sd), c.byref(images[i]), OCTAVES, INIT_BLUR, THRESH, 0.0, False, tmp)
+                counts[i] = sd.numPts
     sampler = ClockSampler(local)
     with quiet_stdout():
         for _ in range(max(1, args.warmup)):
@@ -683,23 +703,23 @@ def run_reference(args):
             mres["n%d" % n] = {"ms": round(ms, 4), "gpair_per_s": round(n * n / (ms * 1e-3) / 1e9, 2)}
             freedata(c.byref(d1)); freedata(c.byref(d2))
         mres["how"] = "reference MatchSiftData (FindMaxCorr10), its own TimerGPU incl. the 5-field D2H copy"
-    value = args.steps * B * world / dt
-    e2e = esteps * B * world / dte
+    value = args.steps * B * R * world / dt
+    e2e = esteps * B * R * world / dte
     if rank == 0:
         print(json.dumps({
             "impl": "reference", "metric": "1920x1080 images/sec ExtractSift", "value": round(value, 1),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dt / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(B, len(imgs), pitch, feats),
+            "config": workload_config(B, len(imgs), pitch, feats, R),
             "api": "unmodified Celebrandil/CudaSift built for sm_100 (oracle/_ref), its own ExtractSift loop as in "
                    "mainSift.cpp:65-69, pre-allocated temp memory, one process per GPU; this process does not load libcudasift_b200.so",
             "clocks": clocks, "numa": numa,
             "cpu_baseline": {"value": round(value, 1), "unit": "images/s", "cores": 1, "kind": "reference",
                              "sample": "the reference is a CUDA library: timed on the GPU (1 host thread drives it), "
-                                       "%d images" % (args.steps * B)},
-            "e2e": {"value": round(e2e, 1), "unit": "images/s", "h2d_bytes_per_step": B * W * H * 4,
-                    "d2h_bytes_per_step": int(B * feats * REC),
+                                       "%d images" % (args.steps * B * R)},
+            "e2e": {"value": round(e2e, 1), "unit": "images/s", "h2d_bytes_per_step": B * R * W * H * 4,
+                    "d2h_bytes_per_step": int(B * R * feats * REC),
                     "api": "CudaImage::Download + ExtractSift (host copy of the points included, cudaSiftH.cu:139-140)"},
             "match": mres,
         }), flush=True)
@@ -714,7 +734,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="images per step per GPU")
+    ap.add_argument("--batch", type=int, default=32, help="device-resident images per GPU (one pass over them = one round)")
+    ap.add_argument("--rounds", type=int, default=0, help="passes over the images per step (0 = enough for a 0.3 s timed region)")
     ap.add_argument("--streams", type=int, default=2, help="batch extractors in flight (batch / streams images each)")
     ap.add_argument("--distinct", type=int, default=8, help="distinct synthetic images per rank")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
