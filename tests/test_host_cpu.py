@@ -116,3 +116,21 @@ def test_demo_png_decoder_matches_opencv(tmp_path):
             assert f.readline() == b"255\n"
             got = np.frombuffer(f.read(), np.uint8).reshape(h, w)
         assert np.array_equal(got, want), name
+
+
+def test_bench_step_definition_is_shared_by_both_arms():
+    """bench.py: both arms derive the passes per step from (steps, batch) by one rule, so the `config` objects the driver
+    compares are identical, and the driver's --steps 20 gives a timed region of >= 7680 images per GPU."""
+    import types
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    head = src.split("# ------------------------------------------------------------------------------------------ host placement")[0]
+    ns = {"__file__": os.path.join(ROOT, "bench.py"), "__name__": "bench_head"}
+    exec(compile(head, "bench_head", "exec"), ns)
+    for steps in (1, 5, 20, 100, 300):
+        a = types.SimpleNamespace(steps=steps, batch=32, rounds=0)
+        r = ns["rounds_per_step"](a)
+        assert steps * 32 * r >= ns["MIN_TIMED_IMAGES"] and (r == 1 or steps * 32 * (r - 1) < ns["MIN_TIMED_IMAGES"])
+        assert ns["workload_config"](32, 8, 1920, 1710.6, r) == ns["workload_config"](32, 8, 1920, 1710.6, r)
+        assert ns["workload_config"](32, 8, 1920, 1710.6, r)["images_per_step_per_gpu"] == 32 * r
+    assert ns["rounds_per_step"](types.SimpleNamespace(steps=20, batch=32, rounds=3)) == 3
