@@ -656,10 +656,10 @@ def run_reference(args):
     tmp = alloc(W, H, OCTAVES, False)
     counts = [0] * B
 
-    R = rounds_per_step(args)
+    NR = rounds_per_step(args)      # passes per step (R is the reference library handle here)
 
     def step(download):
-        for _ in range(R):
+        for _ in range(NR):
             for i in range(B):
                 if download:
                     imgdown(c.byref(images[i]))
@@ -703,23 +703,23 @@ def run_reference(args):
             mres["n%d" % n] = {"ms": round(ms, 4), "gpair_per_s": round(n * n / (ms * 1e-3) / 1e9, 2)}
             freedata(c.byref(d1)); freedata(c.byref(d2))
         mres["how"] = "reference MatchSiftData (FindMaxCorr10), its own TimerGPU incl. the 5-field D2H copy"
-    value = args.steps * B * R * world / dt
-    e2e = esteps * B * R * world / dte
+    value = args.steps * B * NR * world / dt
+    e2e = esteps * B * NR * world / dte
     if rank == 0:
         print(json.dumps({
             "impl": "reference", "metric": "1920x1080 images/sec ExtractSift", "value": round(value, 1),
             "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dt / args.steps * 1e3, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(B, len(imgs), pitch, feats, R),
+            "config": workload_config(B, len(imgs), pitch, feats, NR),
             "api": "unmodified Celebrandil/CudaSift built for sm_100 (oracle/_ref), its own ExtractSift loop as in "
                    "mainSift.cpp:65-69, pre-allocated temp memory, one process per GPU; this process does not load libcudasift_b200.so",
             "clocks": clocks, "numa": numa,
             "cpu_baseline": {"value": round(value, 1), "unit": "images/s", "cores": 1, "kind": "reference",
                              "sample": "the reference is a CUDA library: timed on the GPU (1 host thread drives it), "
-                                       "%d images" % (args.steps * B * R)},
-            "e2e": {"value": round(e2e, 1), "unit": "images/s", "h2d_bytes_per_step": B * R * W * H * 4,
-                    "d2h_bytes_per_step": int(B * R * feats * REC),
+                                       "%d images" % (args.steps * B * NR)},
+            "e2e": {"value": round(e2e, 1), "unit": "images/s", "h2d_bytes_per_step": B * NR * W * H * 4,
+                    "d2h_bytes_per_step": int(B * NR * feats * REC),
                     "api": "CudaImage::Download + ExtractSift (host copy of the points included, cudaSiftH.cu:139-140)"},
             "match": mres,
         }), flush=True)
