@@ -24,7 +24,7 @@ bench)
 ncu)
   echo "== ncu"
   timeout 600 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file gpurun_out/launches_bench.csv \
-      python bench.py --steps 3 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
+      python bench.py --steps 3 --warmup 3 --rounds 1 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
   timeout 600 $NCU --set full --import-source on -k regex:"pyr_|detect|cap32|describe" -s 5 -c 5 -f -o gpurun_out/prof_extract \
       python scripts/r2_prof.py 16 3 > gpurun_out/prof_extract.log 2>&1
   timeout 600 $NCU --set full --import-source on -k regex:"t3_" -s 3 -c 3 -f -o gpurun_out/prof_match \
